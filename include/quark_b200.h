@@ -1,0 +1,172 @@
+/*
+ * libquark_b200 - C ABI of the B200-native QuarkAudio audio-token hot path.
+ *
+ * The reference (alibaba/unified-audio) is pure Python/PyTorch and has no FFI layer; its boundary
+ * for this path is the nn.Module method surface.  The entry points below are what a
+ * Python binding (ctypes) calls from drop-in replacements of
+ *   Codec.encode / Codec.decode            QuarkAudio-HCodec/HCodec-2.0/vq/codec.py:75-99
+ *   ResidualVQ.__call__ / get_output_from_indices (third-party; call sites codec.py:81-82,94-95)
+ *   CustomLlamaModel.llm_forward / LLM_SFT.generate   QuarkAudio-UniSE/model/llm/llm.py:150-228,
+ *                                                     llm_sft.py:93-195
+ * Each op cites the reference lines whose arithmetic it replaces.
+ *
+ * Conventions: every pointer is a DEVICE pointer owned by the caller (row-major, contiguous,
+ * 16-byte aligned) unless stated otherwise; every call is asynchronous on `stream`
+ * (a cudaStream_t passed as void*); return 0 on success, negative on error
+ * (qb_last_error() gives the message; no C++ exception crosses the ABI); no hidden host syncs.
+ *
+ * Activations are channel-last: a tensor [B, T, C] is B*T rows of C contiguous channels.  Dense
+ * contractions take their operands as fp16 "planes": `hi` = rn_fp16(x) and optionally
+ * `lo` = rn_fp16(x - hi).  With both planes of both operands present the GEMM issues
+ * hi*hi + lo*hi + hi*lo on the tensor cores (fp32 accumulate): ~2^-21 relative operand precision.
+ * With `lo` absent it is a single-pass fp16 GEMM (2^-11).  DESIGN.md "precision policy".
+ */
+#ifndef QUARK_B200_H_
+#define QUARK_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint16_t qb_half; /* IEEE fp16 bit pattern */
+
+/* ------------------------------------------------------------------------------------------ */
+const char* qb_last_error(void);
+int qb_version(void);
+/* Number of kernels this library has launched since load / since the last reset (host counter). */
+int64_t qb_launch_count(void);
+void qb_launch_count_reset(void);
+
+/* activation codes for the GEMM epilogue */
+enum { QB_ACT_NONE = 0, QB_ACT_GELU = 1, QB_ACT_SWIGLU = 2, QB_ACT_ELU = 3 };
+
+/* Row mapping of an output / residual tensor: GEMM row (batch b, row m) lives at
+ * ptr + ((b * rows_per_batch + row_off + m) * ld + n).  Lets a GEMM write straight into the
+ * interior of the next convolution's zero-padded channel-last buffer. */
+typedef struct {
+  void* ptr;
+  int64_t ld;
+  int64_t rows_per_batch;
+  int64_t row_off;
+} qb_rowmap;
+
+/*
+ * One dense contraction  D[b, m, n] = sum_{tap, c} A[b, m*stride + tap, c] * W[n, tap*a_ld + c]
+ * i.e. nn.Linear (taps = stride = 1) or a strided nn.Conv1d over a zero-padded channel-last buffer
+ * (vq/conv.py:35-57, vq/semantic_module.py:13-52; weights repacked [Cout, k*Cin_pad] at load).
+ * Epilogue:  v = acc + bias[n];  v = act(v);  v *= gamma[n];  v += residual[b,m,n];
+ *            out_f32 <- v;   out planes <- split_fp16(act2(v))
+ * QB_ACT_SWIGLU pairs columns (2j, 2j+1) -> silu(v[2j]) * v[2j+1] at output column j
+ * (encoder_modules/transformer.py:218-226 with w1/w3 rows interleaved).
+ */
+typedef struct {
+  const qb_half* a_hi;      /* [a_batch, a_rows_per_batch, a_ld] */
+  const qb_half* a_lo;      /* NULL => single-pass */
+  int64_t a_batch;
+  int64_t a_rows_per_batch; /* rows of the (padded) A buffer per batch; multiple of stride */
+  int64_t a_ld;             /* channels per row (multiple of 64) */
+  int32_t taps;
+  int32_t stride;
+  int64_t m_per_batch;      /* output rows per batch */
+  const qb_half* w_hi;      /* [n, taps * a_ld] */
+  const qb_half* w_lo;      /* NULL => single-pass */
+  int64_t n;
+  const float* bias;        /* [n] or NULL */
+  const float* gamma;       /* [n] or NULL */
+  qb_rowmap residual;       /* fp32, ptr NULL => none */
+  int32_t act;              /* QB_ACT_* applied to v before gamma/residual */
+  int32_t act2;             /* QB_ACT_NONE or QB_ACT_ELU, applied only to the fp16-plane output */
+  qb_rowmap out_f32;        /* ptr NULL => not written */
+  qb_rowmap out_hi;         /* fp16 planes; ptr NULL => not written */
+  qb_rowmap out_lo;         /* ptr NULL => hi only (same ld / mapping fields as out_hi required) */
+} qb_gemm_desc;
+
+/* tcgen05 / TMA / TMEM persistent GEMM (the product path). */
+int qb_gemm(const qb_gemm_desc* d, void* stream);
+/* Plain SIMT evaluation of the same descriptor - a device-side cross-check used by tests only. */
+int qb_gemm_simt(const qb_gemm_desc* d, void* stream);
+
+/* ---------------------------------------------------------------- elementwise / normalisation */
+/* x[n] fp32 -> hi/lo planes (lo may be NULL). */
+int qb_split_f16(const float* x, qb_half* hi, qb_half* lo, int64_t n, void* stream);
+/* Copy rows [B, rows, C] fp32 (channel-last) into planes of a padded buffer
+ * [B, rows_per_batch, ld] at row offset row_off; channels C..ld-1 are zeroed; `repeat` repeats each
+ * source row `repeat` times (repeat_interleave, vq/codec_decoder.py:64); act: QB_ACT_NONE / QB_ACT_ELU. */
+int qb_rows_to_planes(const float* x, int64_t B, int64_t rows, int64_t C, int32_t repeat, int32_t act,
+                      qb_half* hi, qb_half* lo, int64_t ld, int64_t rows_per_batch, int64_t row_off, void* stream);
+/* Channel-first [B, C, T] fp32 -> channel-last planes in a padded buffer (semantic features in). */
+int qb_bct_to_planes(const float* x, int64_t B, int64_t C, int64_t T, qb_half* hi, qb_half* lo, int64_t ld,
+                     int64_t rows_per_batch, int64_t row_off, void* stream);
+/* LayerNorm over C (eps) of fp32 rows; writes fp32 and/or planes (any may be NULL).
+ * vq/codec_encoder.py:74,77; vq/codec_decoder.py:67,70 */
+int qb_layernorm(const float* x, const float* w, const float* b, float eps, int64_t B, int64_t rows, int64_t C,
+                 float* out_f32, qb_half* hi, qb_half* lo, int64_t ld, int64_t rows_per_batch, int64_t row_off,
+                 void* stream);
+/* RMSNorm (encoder_modules/transformer.py:77-96) -> planes. */
+int qb_rmsnorm(const float* x, const float* w, float eps, int64_t rows, int64_t C, qb_half* hi, qb_half* lo,
+               void* stream);
+/* ConvNeXt front half: depthwise conv k=7 (zero pad 3) over time + LayerNorm(1e-6) -> planes
+ * (vq/conv.py:201-204).  x [B, T, C] fp32; dw_w [C,7]; dw_b [C]. */
+int qb_dwconv7_ln(const float* x, const float* dw_w, const float* dw_b, const float* ln_w, const float* ln_b,
+                  int64_t B, int64_t T, int64_t C, qb_half* hi, qb_half* lo, void* stream);
+/* GroupNorm(32 groups, eps) statistics then apply (+ optional swish): vq/conv.py:261,286-300.
+ * x [B,T,C] fp32; stats [B,32,2] (mean, rstd).  Output fp32 and/or planes into a padded buffer. */
+int qb_groupnorm_stats(const float* x, int64_t B, int64_t T, int64_t C, int32_t groups, float eps, float* stats,
+                       void* stream);
+int qb_groupnorm_apply(const float* x, const float* stats, const float* w, const float* b, int64_t B, int64_t T,
+                       int64_t C, int32_t groups, int32_t swish, float* out_f32, qb_half* hi, qb_half* lo,
+                       int64_t ld, int64_t rows_per_batch, int64_t row_off, void* stream);
+
+/* ---------------------------------------------------------------- spectral front / back end */
+/* wav [B,T] fp32 -> hop-blocked planes [B, T/hop + 1, hop] with (n_fft-hop)/2 zeros each side
+ * (vq/codec_encoder.py:65-66; frame f = hop blocks f, f+1 when n_fft == 2*hop). */
+int qb_wav_to_hopblocks(const float* wav, int64_t B, int64_t T, int32_t hop, qb_half* hi, qb_half* lo,
+                        void* stream);
+/* spec [M, ld_spec] fp32 = [re_0..re_{nf-1}, im_0..im_{nf-1}] -> log(clip(|S|,1e-5)), angle/pi planes
+ * [B, rows_per_batch, ld] (channels: mag 0..nf-1, phase nf..2nf-1, zero pad); imag of DC/Nyquist
+ * forced to +0 (vq/codec_encoder.py:68-71). */
+int qb_stft_post(const float* spec, int64_t ld_spec, int64_t B, int64_t frames, int32_t nf, qb_half* hi,
+                 qb_half* lo, int64_t ld, int64_t rows_per_batch, int64_t row_off, void* stream);
+/* head output [M, ld_in] fp32 (mag | phase) -> planes [M, ld]: re = min(exp(mag),100)*cos(p),
+ * im = ...*sin(p)   (vq/heads.py:55-65). */
+int qb_istft_pre(const float* head, int64_t ld_in, int64_t M, int32_t nf, qb_half* hi, qb_half* lo, int64_t ld,
+                 void* stream);
+/* windowed frames [B, F, n_fft] fp32 -> overlap-add (hop = n_fft/2), trim, / window envelope
+ * -> wav [B, F*hop]   (vq/spectral_ops.py:56-73). */
+int qb_istft_ola(const float* frames, const float* window, int64_t B, int64_t F, int32_t n_fft, float* wav,
+                 void* stream);
+
+/* ---------------------------------------------------------------- sequence ops */
+/* Non-causal multi-head attention with RoPE applied to q,k on load
+ * (encoder_modules/transformer.py:134-182).  qkv [B,T,3*H*D] fp32 (q|k|v), D = 64.  Output planes. */
+int qb_attention(const float* qkv, int64_t B, int64_t T, int32_t heads, const float* rope_cos,
+                 const float* rope_sin, qb_half* out_hi, qb_half* out_lo, void* stream);
+/* Single-layer LSTM recurrence (encoder_modules/transformer.py:115,133): xp [B,T,4H] fp32 already
+ * holds x W_ih^T + b_ih + b_hh; w_hh planes [4H, H]; output h planes [B,T,H].
+ * workspace: qb_lstm_workspace_bytes(B,H). */
+int64_t qb_lstm_workspace_bytes(int64_t B, int64_t H);
+int qb_lstm(const float* xp, const qb_half* whh_hi, const qb_half* whh_lo, int64_t B, int64_t T, int64_t H,
+            qb_half* out_hi, qb_half* out_lo, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------- residual vector quantiser */
+/* x [M,D] fp32, codebooks [nq,K,D] fp32 (+ their fp16 planes cb_hi/cb_lo [nq,K,D]) -> idx [M,nq] int64
+ * (+ optional quantized [M,D]).  Per layer: scores |e|^2 - 2 r.e on the tensor cores (3-term split),
+ * arg-min with an exact fp64 re-rank of every candidate within tolerance of the minimum, lowest index
+ * wins exact ties; residual updated in fp32 (codec.py:81-82; core_vq.py:223-238,394-412).
+ * neg_half_e2: [nq*K] values -|e|^2/2 followed by K values of -2.0 (epilogue constants);
+ * e2max = max_j |e_j|^2 (tolerance scale).  workspace: qb_rvq_workspace_bytes(M,D,K). */
+int64_t qb_rvq_workspace_bytes(int64_t M, int32_t D, int32_t K);
+int qb_rvq_encode(const float* x, const float* codebooks, const qb_half* cb_hi, const qb_half* cb_lo,
+                  const float* neg_half_e2, float e2max, int64_t M, int32_t D, int32_t K, int32_t nq,
+                  int64_t* idx, float* quantized, void* workspace, void* stream);
+/* idx [M,nq] int64 (-1 = dropped) -> out[M, out_ld] (+ col_off) = sum_q codebooks[q][idx_q]
+ * summed q = 0..nq-1 in fp32 (codec.py:94-95). */
+int qb_rvq_decode(const int64_t* idx, const float* codebooks, int64_t M, int32_t D, int32_t K, int32_t nq,
+                  float* out, int64_t out_ld, int64_t col_off, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUARK_B200_H_ */

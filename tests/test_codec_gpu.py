@@ -1,0 +1,129 @@
+"""GPU parity of unified_audio_b200.Codec (through the C ABI) against the CPU oracle and the golden
+fixtures generated from the reference's own modules (oracle/make_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-3     # north_star: floats within 1e-3 relative
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def build(cfg, seed, precision):
+    from oracle import weights
+    from unified_audio_b200.codec import Codec
+    sd = weights.make_h2_state_dict(cfg, seed)
+    m = Codec(cfg["encoder_config"], cfg["decoder_config"], cfg["quantizer_config"], cfg["semantic_encoder_config"],
+              cfg["semantic_decoder_config"], precision=precision)
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    return m.cuda(), sd
+
+
+def golden(name):
+    z = np.load(os.path.join(GOLD, f"h2_{name}.npz"))
+    meta = json.loads(str(z["meta"]))
+    return z, meta
+
+
+def check_codes(tag, got, want, x_rows, codebooks):
+    """indices must equal the oracle's wherever the fp64 margin of the decision is numerically safe"""
+    from oracle import rvq
+    B, nq, N = want.shape
+    got_r = got.cpu().transpose(1, 2).reshape(B * N, nq)
+    want_r = want.transpose(1, 2).reshape(B * N, nq)
+    _, margin = rvq.rvq_margin_audit(x_rows, codebooks, want_r)
+    first_bad = torch.full((B * N,), nq, dtype=torch.long)
+    for q in range(nq - 1, -1, -1):
+        first_bad[got_r[:, q] != want_r[:, q]] = q
+    n_tok_bad = int((first_bad < nq).sum())
+    worst = [float(margin[i, first_bad[i]]) for i in range(B * N) if first_bad[i] < nq]
+    print(f"[{tag}] tokens with a differing index: {n_tok_bad}/{B*N}; margins at first divergence: {worst[:8]}")
+    return n_tok_bad, worst
+
+
+@pytest.mark.parametrize("name,precision", [("small", "accurate"), ("small", "mixed"), ("mid", "mixed")])
+def test_h2_golden(lib, name, precision):
+    from oracle import hcodec2, weights
+    z, meta = golden(name)
+    cfg = meta["cfg"]
+    model, sd = build(cfg, meta["seed_w"], precision)
+    wav, feat = weights.synth_inputs(cfg, meta["batch"], meta["n_tokens"], meta["seed_x"])
+    # stage-wise taps vs the oracle (diagnostic + assertion)
+    otaps = {}
+    hcodec2.codec_encode(sd, cfg, wav, feat, taps=otaps)
+    gtaps = {}
+    ac, sc = model.encode(wav.cuda(), feat.cuda(), taps=gtaps)
+    torch.cuda.synchronize()
+    for k in otaps:
+        if k in gtaps:
+            a, b = gtaps[k].float().cpu(), otaps[k]
+            if k == "enc.feat":   # phase wraps at +-1: compare on the circle
+                nf = b.shape[1] // 2
+                d = (a[:, nf:] - b[:, nf:] + 1) % 2 - 1
+                print(f"  tap {k}: mag rel {rel(a[:, :nf], b[:, :nf]):.2e} phase max|d| {float(d.abs().max()):.2e}")
+            else:
+                print(f"  tap {k}: max-rel {rel(a, b):.2e}  l2-rel {l2(a, b):.2e}")
+    emb_ref, sem_ref = torch.from_numpy(z["emb"]), torch.from_numpy(z["sem"])
+    e_emb, e_sem = rel(gtaps["enc.out"], emb_ref), rel(gtaps["sem.out"], sem_ref)
+    print(f"[{name}/{precision}] emb rel {e_emb:.2e} sem rel {e_sem:.2e}")
+    assert e_emb < TOL and e_sem < TOL
+    # codes: RVQ on the ORACLE embedding must be bit-exact; end-to-end codes reported with margins
+    B, D, N = emb_ref.shape
+    cb_a, cb_s = hcodec2._codebooks(sd, "quantizer"), hcodec2._codebooks(sd, "semantic_quantizer")
+    rows_a = emb_ref.transpose(1, 2).reshape(B * N, D)
+    ia, _ = model.quantizer.encode_rows(rows_a.cuda())
+    want_a = torch.from_numpy(z["acoustic_codes"])
+    nbad, worst = check_codes("rvq on oracle emb", ia.reshape(B, N, -1).transpose(1, 2), want_a, rows_a, cb_a)
+    assert nbad == 0 or max(worst) < 1e-5
+    check_codes("end-to-end acoustic", ac, want_a, rows_a, cb_a)
+    check_codes("end-to-end semantic", sc, torch.from_numpy(z["semantic_codes"]),
+                sem_ref.transpose(1, 2).reshape(B * N, D), cb_s)
+    # decode from the reference's codes
+    dtaps, odtaps = {}, {}
+    rec = model.decode(want_a.cuda(), torch.from_numpy(z["semantic_codes"]).cuda(), taps=dtaps)
+    torch.cuda.synchronize()
+    hcodec2.codec_decode(sd, cfg, want_a, torch.from_numpy(z["semantic_codes"]), taps=odtaps)
+    for k in odtaps:
+        if k in dtaps:
+            print(f"  tap {k}: max-rel {rel(dtaps[k].float(), odtaps[k]):.2e}  l2-rel {l2(dtaps[k].float(), odtaps[k]):.2e}")
+    e_wav = rel(rec, torch.from_numpy(z["wav_rec"]))
+    print(f"[{name}/{precision}] wav rel {e_wav:.2e}  l2 {l2(rec, torch.from_numpy(z['wav_rec'])):.2e}")
+    assert rec.shape == z["wav_rec"].shape
+    assert e_wav < TOL
+
+
+def test_h2_full_config_vs_oracle(lib):
+    """Shipped 48 kHz config (large_12.5hz_config.yaml), B=2 x 8 tokens, mixed precision policy."""
+    from oracle import hcodec2, weights
+    cfg = weights.H2_FULL
+    model, sd = build(cfg, 0, "mixed")
+    wav, feat = weights.synth_inputs(cfg, 2, 8, 2000)
+    otaps, gtaps = {}, {}
+    oa, os_ = hcodec2.codec_encode(sd, cfg, wav, feat, taps=otaps)
+    ac, sc = model.encode(wav.cuda(), feat.cuda(), taps=gtaps)
+    torch.cuda.synchronize()
+    for k in otaps:
+        if k in gtaps and k != "enc.feat":
+            print(f"  tap {k}: max-rel {rel(gtaps[k].float(), otaps[k]):.2e}")
+    assert rel(gtaps["enc.out"], otaps["enc.out"]) < TOL and rel(gtaps["sem.out"], otaps["sem.out"]) < TOL
+    B, D, N = otaps["enc.out"].shape
+    check_codes("full end-to-end acoustic", ac, oa, otaps["enc.out"].transpose(1, 2).reshape(B * N, D),
+                hcodec2._codebooks(sd, "quantizer"))
+    rec = model.decode(oa.cuda(), os_.cuda())
+    torch.cuda.synchronize()
+    ref = hcodec2.codec_decode(sd, cfg, oa, os_)
+    print(f"[full/mixed] wav rel {rel(rec, ref):.2e} l2 {l2(rec, ref):.2e}")
+    assert rel(rec, ref) < TOL

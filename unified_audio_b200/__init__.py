@@ -1,0 +1,8 @@
+"""unified_audio_b200 - B200-native (sm_100a) implementation of QuarkAudio's audio-token hot path.
+
+Public surface mirrors the reference (alibaba/unified-audio):
+  Codec            <- QuarkAudio-HCodec/HCodec-2.0/vq/codec.py:17   (encode / decode)
+  ResidualVQ       <- vector_quantize_pytorch.ResidualVQ as the reference constructs it
+Kernels live in csrc/ behind the C ABI of include/quark_b200.h (lib/libquark_b200.so).
+"""
+__version__ = "0.1.0"

@@ -1,0 +1,82 @@
+"""ctypes binding of libquark_b200.so (the C ABI declared in include/quark_b200.h).
+
+The library is built in-tree by unified_audio_b200/build.py (nvcc, sm_100a).  There is NO fallback:
+if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libquark_b200.so")
+
+ACT_NONE, ACT_GELU, ACT_SWIGLU, ACT_ELU = 0, 1, 2, 3
+
+
+class RowMap(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("ld", C.c_int64), ("rows_per_batch", C.c_int64), ("row_off", C.c_int64)]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("a_batch", C.c_int64), ("a_rows_per_batch", C.c_int64),
+        ("a_ld", C.c_int64), ("taps", C.c_int32), ("stride", C.c_int32), ("m_per_batch", C.c_int64),
+        ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("n", C.c_int64), ("bias", C.c_void_p), ("gamma", C.c_void_p),
+        ("residual", RowMap), ("act", C.c_int32), ("act2", C.c_int32), ("out_f32", RowMap), ("out_hi", RowMap),
+        ("out_lo", RowMap),
+    ]
+
+
+# name -> (restype, argtypes); mirrors include/quark_b200.h one to one
+_vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+SIGNATURES = {
+    "qb_last_error": (C.c_char_p, []),
+    "qb_version": (C.c_int, []),
+    "qb_launch_count": (C.c_int64, []),
+    "qb_launch_count_reset": (None, []),
+    "qb_gemm": (C.c_int, [C.POINTER(GemmDesc), _vp]),
+    "qb_gemm_simt": (C.c_int, [C.POINTER(GemmDesc), _vp]),
+    "qb_split_f16": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "qb_rows_to_planes": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "qb_bct_to_planes": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "qb_layernorm": (C.c_int, [_vp, _vp, _vp, _f32, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "qb_rmsnorm": (C.c_int, [_vp, _vp, _f32, _i64, _i64, _vp, _vp, _vp]),
+    "qb_dwconv7_ln": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "qb_groupnorm_stats": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _f32, _vp, _vp]),
+    "qb_groupnorm_apply": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _i64,
+                                      _i64, _vp]),
+    "qb_wav_to_hopblocks": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp]),
+    "qb_stft_post": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "qb_istft_pre": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _vp]),
+    "qb_istft_ola": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp]),
+    "qb_attention": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "qb_lstm_workspace_bytes": (C.c_int64, [_i64, _i64]),
+    "qb_lstm": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "qb_rvq_workspace_bytes": (C.c_int64, [_i64, _i32, _i32]),
+    "qb_rvq_encode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "qb_rvq_decode": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _i64, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found - build it with `python -m unified_audio_b200.build` "
+                "(there is no CPU / PyTorch fallback for the product path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(code: int):
+    if code != 0:
+        raise RuntimeError(f"libquark_b200 error {code}: {load().qb_last_error().decode()}")

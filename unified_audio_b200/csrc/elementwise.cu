@@ -1,0 +1,359 @@
+// Memory-bound kernels of the H-Codec path: plane conversion, normalisations, ConvNeXt depthwise
+// front half, spectral pre/post-processing.  All are HBM/L2-bound; design rules: channel-last rows,
+// 128-bit vector accesses along C, one warp (or block) per row, fp32 statistics (two-pass).
+#include <atomic>
+
+#include "common.cuh"
+#include "quark_b200.h"
+
+namespace qb {
+extern std::atomic<long long> g_launches;
+
+#define QB_LAUNCH_END()            \
+  g_launches++;                    \
+  QB_CHECK_CUDA(cudaGetLastError()); \
+  return 0
+
+__device__ __forceinline__ void store_planes(__half* hi, __half* lo, long long o, float v) {
+  __half h, l;
+  split_f16(v, h, l);
+  hi[o] = h;
+  if (lo) lo[o] = l;
+}
+
+// ------------------------------------------------------------------ split
+__global__ void split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) store_planes(hi, lo, i, x[i]);
+}
+
+// ------------------------------------------------------------------ rows -> planes (padded buffer)
+__global__ void rows_to_planes_kernel(const float* __restrict__ x, int rows, int C, int repeat, int act,
+                                      __half* __restrict__ hi, __half* __restrict__ lo, long long ld, long long rpb,
+                                      long long off) {
+  const int r_out = blockIdx.x, b = blockIdx.y;
+  const float* src = x + ((long long)b * rows + r_out / repeat) * C;
+  const long long o = ((long long)b * rpb + off + r_out) * ld;
+  for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+    float v = c < C ? src[c] : 0.f;
+    if (act == QB_ACT_ELU) v = elu_f(v);
+    store_planes(hi, lo, o + c, v);
+  }
+}
+
+__global__ void bct_to_planes_kernel(const float* __restrict__ x, int C, int T, __half* __restrict__ hi,
+                                     __half* __restrict__ lo, long long ld, long long rpb, long long off) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < T) ? x[((long long)b * C + c) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < T && c < ld) store_planes(hi, lo, ((long long)b * rpb + off + t) * ld + c, c < C ? tile[threadIdx.x][i] : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm / RMSNorm (warp per row)
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bz,
+                                 float eps, long long rows_total, int rows, int C, float* __restrict__ out,
+                                 __half* __restrict__ hi, __half* __restrict__ lo, long long ld, long long rpb,
+                                 long long off) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows_total) return;
+  const float* xr = x + row * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) { float d = xr[c] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  const long long b = row / rows, r = row % rows;
+  const long long o = (b * rpb + off + r) * ld;
+  for (int c = lane; c < C; c += 32) {
+    float v = (xr[c] - mean) * rstd * w[c] + bz[c];
+    if (out) out[row * C + c] = v;
+    if (hi) store_planes(hi, lo, o + c, v);
+  }
+}
+
+__global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, float eps, long long rows, int C,
+                               __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) q += xr[c] * xr[c];
+  const float r = rsqrtf(warp_sum(q) / C + eps);
+  for (int c = lane; c < C; c += 32) store_planes(hi, lo, row * C + c, xr[c] * r * w[c]);
+}
+
+// ------------------------------------------------------------------ ConvNeXt: dwconv k7 + LayerNorm
+// One warp per (b,t) row; the 7 input rows come from L1/L2 (neighbouring warps of the block share
+// them).  dw_w is [C,7] as the reference stores it (conv.weight[C,1,7]).
+__global__ void dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ dw_w,
+                                  const float* __restrict__ dw_b, const float* __restrict__ ln_w,
+                                  const float* __restrict__ ln_b, int T, int C, long long rows_total,
+                                  __half* __restrict__ hi, __half* __restrict__ lo) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + wi;
+  if (row >= rows_total) return;
+  float* y = sm + (size_t)wi * C;
+  const int t = (int)(row % T);
+  const float* xb = x + (row - t) * C;  // start of this clip
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    float acc = dw_b[c];
+    const float* wc = dw_w + (long long)c * 7;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      int tt = t + j - 3;
+      if (tt >= 0 && tt < T) acc = fmaf(wc[j], xb[(long long)tt * C + c], acc);
+    }
+    y[c] = acc;
+    s += acc;
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) { float d = y[c] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) / C + 1e-6f);
+  for (int c = lane; c < C; c += 32) store_planes(hi, lo, row * C + c, (y[c] - mean) * rstd * ln_w[c] + ln_b[c]);
+}
+
+// ------------------------------------------------------------------ GroupNorm
+__global__ void groupnorm_stats_kernel(const float* __restrict__ x, int T, int C, int G, float eps,
+                                       float* __restrict__ stats) {
+  const int g = blockIdx.x, b = blockIdx.y, cpg = C / G;
+  const float* xb = x + (long long)b * T * C + g * cpg;
+  const int n = T * cpg;
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float v = xb[(long long)(i / cpg) * C + (i % cpg)];
+    s += v;
+    q += (double)v * v;
+  }
+  __shared__ double ss[32], sq[32];
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sq[threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S = 0, Q = 0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) { S += ss[i]; Q += sq[i]; }
+    double mean = S / n, var = Q / n - mean * mean;
+    if (var < 0) var = 0;
+    stats[((long long)b * G + g) * 2] = (float)mean;
+    stats[((long long)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+__global__ void groupnorm_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+                                       const float* __restrict__ w, const float* __restrict__ bz, int T, int C, int G,
+                                       int swish, float* __restrict__ out, __half* __restrict__ hi,
+                                       __half* __restrict__ lo, long long ld, long long rpb, long long off) {
+  const int t = blockIdx.x, b = blockIdx.y, cpg = C / G;
+  const long long ri = ((long long)b * T + t) * C, ro = ((long long)b * rpb + off + t) * ld;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* st = stats + ((long long)b * G + c / cpg) * 2;
+    float v = (x[ri + c] - st[0]) * st[1] * w[c] + bz[c];
+    if (swish) v = v * sigmoid_acc(v);
+    if (out) out[ri + c] = v;
+    if (hi) store_planes(hi, lo, ro + c, v);
+  }
+}
+
+// ------------------------------------------------------------------ spectral
+__global__ void wav_to_hopblocks_kernel(const float* __restrict__ wav, long long T, int hop, int pad,
+                                        __half* __restrict__ hi, __half* __restrict__ lo, long long per_batch) {
+  const int b = blockIdx.y;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per_batch) return;
+  long long src = i - pad;
+  float v = (src >= 0 && src < T) ? wav[(long long)b * T + src] : 0.f;
+  store_planes(hi, lo, (long long)b * per_batch + i, v);
+}
+
+__global__ void stft_post_kernel(const float* __restrict__ spec, long long ld_spec, int frames, int nf,
+                                 __half* __restrict__ hi, __half* __restrict__ lo, long long ld, long long rpb,
+                                 long long off) {
+  const int f = blockIdx.x, b = blockIdx.y;
+  const float* sp = spec + ((long long)b * frames + f) * ld_spec;
+  const long long o = ((long long)b * rpb + off + f) * ld;
+  for (int k = threadIdx.x; k < ld; k += blockDim.x) {
+    if (k < nf) {
+      float re = sp[k], im = (k == 0 || k == nf - 1) ? 0.f : sp[nf + k];
+      float mag = hypotf(re, im);
+      store_planes(hi, lo, o + k, logf(fmaxf(mag, 1e-5f)));
+      store_planes(hi, lo, o + nf + k, atan2f(im, re) * 0.31830988618379067154f);
+    } else if (k >= 2 * nf) {
+      store_planes(hi, lo, o + k, 0.f);
+    }
+  }
+}
+
+__global__ void istft_pre_kernel(const float* __restrict__ head, long long ld_in, int nf, __half* __restrict__ hi,
+                                 __half* __restrict__ lo, long long ld) {
+  const long long m = blockIdx.x;
+  const float* hp = head + m * ld_in;
+  const long long o = m * ld;
+  for (int k = threadIdx.x; k < ld; k += blockDim.x) {
+    if (k < nf) {
+      float mag = fminf(expf(hp[k]), 100.f), ph = hp[nf + k];
+      float sn, cs;
+      sincosf(ph, &sn, &cs);
+      store_planes(hi, lo, o + k, mag * cs);
+      store_planes(hi, lo, o + nf + k, mag * sn);
+    } else if (k >= 2 * nf) {
+      store_planes(hi, lo, o + k, 0.f);
+    }
+  }
+}
+
+__global__ void istft_ola_kernel(const float* __restrict__ frames, const float* __restrict__ window, int F, int n_fft,
+                                 float* __restrict__ wav) {
+  const int hop = n_fft / 2, pad = (n_fft - hop) / 2;
+  const int b = blockIdx.y;
+  const long long len = (long long)F * hop;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= len) return;
+  const long long u = t + pad;
+  const int f1 = (int)(u / hop), f0 = f1 - 1;
+  float acc = 0.f, env = 0.f;
+  if (f0 >= 0 && f0 < F) {
+    int i = (int)(u - (long long)f0 * hop);
+    acc += frames[((long long)b * F + f0) * n_fft + i];
+    env += window[i] * window[i];
+  }
+  if (f1 < F) {
+    int i = (int)(u - (long long)f1 * hop);
+    acc += frames[((long long)b * F + f1) * n_fft + i];
+    env += window[i] * window[i];
+  }
+  wav[(long long)b * len + t] = acc / env;
+}
+
+}  // namespace qb
+using namespace qb;
+
+extern "C" int qb_split_f16(const float* x, qb_half* hi, qb_half* lo, int64_t n, void* stream) {
+  QB_REQUIRE(x && hi && n >= 0, "split: bad args");
+  if (n == 0) return 0;
+  int blocks = (int)(ceil_div(n, 256) < 148 * 16 ? ceil_div(n, 256) : 148 * 16);
+  split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__half*)hi, (__half*)lo, n);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_rows_to_planes(const float* x, int64_t B, int64_t rows, int64_t C, int32_t repeat, int32_t act,
+                                 qb_half* hi, qb_half* lo, int64_t ld, int64_t rows_per_batch, int64_t row_off,
+                                 void* stream) {
+  QB_REQUIRE(x && hi && repeat >= 1 && C <= ld, "rows_to_planes: bad args");
+  QB_REQUIRE(row_off + rows * repeat <= rows_per_batch, "rows_to_planes: rows overflow the padded buffer");
+  dim3 grid((unsigned)(rows * repeat), (unsigned)B);
+  rows_to_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (int)rows, (int)C, repeat, act, (__half*)hi,
+                                                               (__half*)lo, ld, rows_per_batch, row_off);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_bct_to_planes(const float* x, int64_t B, int64_t C, int64_t T, qb_half* hi, qb_half* lo, int64_t ld,
+                                int64_t rows_per_batch, int64_t row_off, void* stream) {
+  QB_REQUIRE(x && hi && C <= ld && row_off + T <= rows_per_batch, "bct_to_planes: bad args");
+  dim3 grid((unsigned)ceil_div(T, 32), (unsigned)ceil_div(ld, 32), (unsigned)B), block(32, 8);
+  bct_to_planes_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, (int)C, (int)T, (__half*)hi, (__half*)lo, ld,
+                                                                rows_per_batch, row_off);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_layernorm(const float* x, const float* w, const float* b, float eps, int64_t B, int64_t rows,
+                            int64_t C, float* out_f32, qb_half* hi, qb_half* lo, int64_t ld, int64_t rows_per_batch,
+                            int64_t row_off, void* stream) {
+  QB_REQUIRE(x && w && b && (out_f32 || hi), "layernorm: bad args");
+  QB_REQUIRE(!hi || (C <= ld && row_off + rows <= rows_per_batch), "layernorm: plane buffer too small");
+  const long long total = B * rows;
+  layernorm_kernel<<<(unsigned)ceil_div(total, 8), 256, 0, (cudaStream_t)stream>>>(
+      x, w, b, eps, total, (int)rows, (int)C, out_f32, (__half*)hi, (__half*)lo, ld, rows_per_batch, row_off);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_rmsnorm(const float* x, const float* w, float eps, int64_t rows, int64_t C, qb_half* hi, qb_half* lo,
+                          void* stream) {
+  QB_REQUIRE(x && w && hi, "rmsnorm: bad args");
+  rmsnorm_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, w, eps, rows, (int)C, (__half*)hi,
+                                                                                 (__half*)lo);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_dwconv7_ln(const float* x, const float* dw_w, const float* dw_b, const float* ln_w,
+                             const float* ln_b, int64_t B, int64_t T, int64_t C, qb_half* hi, qb_half* lo,
+                             void* stream) {
+  QB_REQUIRE(x && dw_w && dw_b && ln_w && ln_b && hi, "dwconv7_ln: bad args");
+  const int warps = 8;
+  const size_t smem = (size_t)warps * C * sizeof(float);
+  QB_REQUIRE(smem <= 200 * 1024, "dwconv7_ln: C too large");
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    QB_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  const long long total = B * T;
+  dwconv7_ln_kernel<<<(unsigned)ceil_div(total, warps), warps * 32, smem, (cudaStream_t)stream>>>(
+      x, dw_w, dw_b, ln_w, ln_b, (int)T, (int)C, total, (__half*)hi, (__half*)lo);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_groupnorm_stats(const float* x, int64_t B, int64_t T, int64_t C, int32_t groups, float eps,
+                                  float* stats, void* stream) {
+  QB_REQUIRE(x && stats && C % groups == 0, "groupnorm_stats: bad args");
+  dim3 grid((unsigned)groups, (unsigned)B);
+  groupnorm_stats_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(x, (int)T, (int)C, groups, eps, stats);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_groupnorm_apply(const float* x, const float* stats, const float* w, const float* b, int64_t B,
+                                  int64_t T, int64_t C, int32_t groups, int32_t swish, float* out_f32, qb_half* hi,
+                                  qb_half* lo, int64_t ld, int64_t rows_per_batch, int64_t row_off, void* stream) {
+  QB_REQUIRE(x && stats && w && b && (out_f32 || hi), "groupnorm_apply: bad args");
+  QB_REQUIRE(!hi || (C <= ld && row_off + T <= rows_per_batch), "groupnorm_apply: plane buffer too small");
+  dim3 grid((unsigned)T, (unsigned)B);
+  groupnorm_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, stats, w, b, (int)T, (int)C, groups, swish, out_f32,
+                                                                (__half*)hi, (__half*)lo, ld, rows_per_batch, row_off);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_wav_to_hopblocks(const float* wav, int64_t B, int64_t T, int32_t hop, qb_half* hi, qb_half* lo,
+                                   void* stream) {
+  QB_REQUIRE(wav && hi && T % hop == 0, "wav_to_hopblocks: T must be a multiple of hop");
+  const long long per_batch = T + hop;
+  dim3 grid((unsigned)ceil_div(per_batch, 256), (unsigned)B);
+  wav_to_hopblocks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(wav, T, hop, hop / 2, (__half*)hi, (__half*)lo,
+                                                                 per_batch);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_stft_post(const float* spec, int64_t ld_spec, int64_t B, int64_t frames, int32_t nf, qb_half* hi,
+                            qb_half* lo, int64_t ld, int64_t rows_per_batch, int64_t row_off, void* stream) {
+  QB_REQUIRE(spec && hi && 2 * nf <= ld && 2 * nf <= ld_spec && row_off + frames <= rows_per_batch, "stft_post: bad args");
+  dim3 grid((unsigned)frames, (unsigned)B);
+  stft_post_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(spec, ld_spec, (int)frames, nf, (__half*)hi, (__half*)lo, ld,
+                                                          rows_per_batch, row_off);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_istft_pre(const float* head, int64_t ld_in, int64_t M, int32_t nf, qb_half* hi, qb_half* lo,
+                            int64_t ld, void* stream) {
+  QB_REQUIRE(head && hi && 2 * nf <= ld && 2 * nf <= ld_in, "istft_pre: bad args");
+  istft_pre_kernel<<<(unsigned)M, 256, 0, (cudaStream_t)stream>>>(head, ld_in, nf, (__half*)hi, (__half*)lo, ld);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_istft_ola(const float* frames, const float* window, int64_t B, int64_t F, int32_t n_fft, float* wav,
+                            void* stream) {
+  QB_REQUIRE(frames && window && wav && n_fft % 4 == 0, "istft_ola: bad args");
+  dim3 grid((unsigned)ceil_div(F * (n_fft / 2), 256), (unsigned)B);
+  istft_ola_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames, window, (int)F, n_fft, wav);
+  QB_LAUNCH_END();
+}

@@ -1,0 +1,174 @@
+"""Torch-tensor front ends of the C-ABI ops.  PyTorch here is device memory + streams only: every
+function hands raw device pointers to libquark_b200 on the current CUDA stream."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_ELU, ACT_GELU, ACT_NONE, ACT_SWIGLU, GemmDesc, RowMap  # noqa: F401
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "libquark_b200 needs contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+@dataclass
+class Planes:
+    """fp16 hi (+ optional lo) planes of a channel-last activation / weight."""
+    hi: torch.Tensor
+    lo: Optional[torch.Tensor] = None
+
+    @staticmethod
+    def zeros(shape, split: bool, device):
+        hi = torch.zeros(shape, dtype=torch.float16, device=device)
+        return Planes(hi, torch.zeros(shape, dtype=torch.float16, device=device) if split else None)
+
+    @staticmethod
+    def from_f32(x: torch.Tensor, split: bool = True):
+        """Load-time helper (weights): hi = rn_fp16(x) saturated, lo = rn_fp16(x - hi)."""
+        x = x.float().clamp(-65504.0, 65504.0)
+        hi = x.half()
+        lo = (x - hi.float()).half() if split else None
+        return Planes(hi.contiguous(), lo.contiguous() if lo is not None else None)
+
+    def float(self):
+        return self.hi.float() + (self.lo.float() if self.lo is not None else 0.0)
+
+
+def rowmap(t: Optional[torch.Tensor], ld=0, rows_per_batch=0, row_off=0) -> RowMap:
+    return RowMap(_p(t), ld, rows_per_batch, row_off)
+
+
+def gemm(a: Planes, w: Planes, n: int, *, a_batch: int, a_rows_per_batch: int, a_ld: int, m_per_batch: int,
+         taps: int = 1, stride: int = 1, bias=None, gamma=None, residual: Optional[RowMap] = None, act=ACT_NONE,
+         act2=ACT_NONE, out_f32: Optional[RowMap] = None, out_planes: Optional[Planes] = None,
+         out_planes_map=(0, 0, 0), simt: bool = False):
+    """One dense contraction (see qb_gemm_desc).  Split mode iff both a.lo and w.lo are given."""
+    split = a.lo is not None and w.lo is not None
+    d = GemmDesc()
+    d.a_hi, d.a_lo = _p(a.hi), (_p(a.lo) if split else None)
+    d.a_batch, d.a_rows_per_batch, d.a_ld = a_batch, a_rows_per_batch, a_ld
+    d.taps, d.stride, d.m_per_batch = taps, stride, m_per_batch
+    d.w_hi, d.w_lo, d.n = _p(w.hi), (_p(w.lo) if split else None), n
+    d.bias, d.gamma = _p(bias), _p(gamma)
+    d.residual = residual if residual is not None else RowMap(None, 0, 0, 0)
+    d.act, d.act2 = act, act2
+    d.out_f32 = out_f32 if out_f32 is not None else RowMap(None, 0, 0, 0)
+    if out_planes is not None:
+        ld, rpb, off = out_planes_map
+        d.out_hi = RowMap(_p(out_planes.hi), ld, rpb, off)
+        d.out_lo = RowMap(_p(out_planes.lo), ld, rpb, off) if out_planes.lo is not None else RowMap(None, 0, 0, 0)
+    else:
+        d.out_hi = RowMap(None, 0, 0, 0)
+        d.out_lo = RowMap(None, 0, 0, 0)
+    lib = _lib.load()
+    _lib.check((lib.qb_gemm_simt if simt else lib.qb_gemm)(C.byref(d), _stream()))
+
+
+def split_f16(x: torch.Tensor, out: Planes):
+    _lib.check(_lib.load().qb_split_f16(_p(x), _p(out.hi), _p(out.lo), x.numel(), _stream()))
+
+
+def rows_to_planes(x, B, rows, Cc, out: Planes, ld, rows_per_batch, row_off, repeat=1, act=ACT_NONE):
+    _lib.check(_lib.load().qb_rows_to_planes(_p(x), B, rows, Cc, repeat, act, _p(out.hi), _p(out.lo), ld,
+                                             rows_per_batch, row_off, _stream()))
+
+
+def bct_to_planes(x, out: Planes, ld, rows_per_batch, row_off):
+    B, Cc, T = x.shape
+    _lib.check(_lib.load().qb_bct_to_planes(_p(x), B, Cc, T, _p(out.hi), _p(out.lo), ld, rows_per_batch, row_off,
+                                            _stream()))
+
+
+def layernorm(x, w, b, B, rows, Cc, eps=1e-6, out_f32=None, out: Optional[Planes] = None, ld=0, rows_per_batch=0,
+              row_off=0):
+    hi = out.hi if out is not None else None
+    lo = out.lo if out is not None else None
+    if out is not None and ld == 0:
+        ld, rows_per_batch, row_off = Cc, rows, 0
+    _lib.check(_lib.load().qb_layernorm(_p(x), _p(w), _p(b), eps, B, rows, Cc, _p(out_f32), _p(hi), _p(lo), ld,
+                                        rows_per_batch, row_off, _stream()))
+
+
+def rmsnorm(x, w, rows, Cc, out: Planes, eps=1e-6):
+    _lib.check(_lib.load().qb_rmsnorm(_p(x), _p(w), eps, rows, Cc, _p(out.hi), _p(out.lo), _stream()))
+
+
+def dwconv7_ln(x, dw_w, dw_b, ln_w, ln_b, B, T, Cc, out: Planes):
+    _lib.check(_lib.load().qb_dwconv7_ln(_p(x), _p(dw_w), _p(dw_b), _p(ln_w), _p(ln_b), B, T, Cc, _p(out.hi), _p(out.lo),
+                                         _stream()))
+
+
+def groupnorm_stats(x, B, T, Cc, stats, groups=32, eps=1e-6):
+    _lib.check(_lib.load().qb_groupnorm_stats(_p(x), B, T, Cc, groups, eps, _p(stats), _stream()))
+
+
+def groupnorm_apply(x, stats, w, b, B, T, Cc, swish, out_f32=None, out: Optional[Planes] = None, ld=0,
+                    rows_per_batch=0, row_off=0, groups=32):
+    hi = out.hi if out is not None else None
+    lo = out.lo if out is not None else None
+    _lib.check(_lib.load().qb_groupnorm_apply(_p(x), _p(stats), _p(w), _p(b), B, T, Cc, groups, int(swish), _p(out_f32),
+                                              _p(hi), _p(lo), ld, rows_per_batch, row_off, _stream()))
+
+
+def wav_to_hopblocks(wav, hop, out: Planes):
+    B, T = wav.shape
+    _lib.check(_lib.load().qb_wav_to_hopblocks(_p(wav), B, T, hop, _p(out.hi), _p(out.lo), _stream()))
+
+
+def stft_post(spec, ld_spec, B, frames, nf, out: Planes, ld, rows_per_batch, row_off):
+    _lib.check(_lib.load().qb_stft_post(_p(spec), ld_spec, B, frames, nf, _p(out.hi), _p(out.lo), ld, rows_per_batch,
+                                        row_off, _stream()))
+
+
+def istft_pre(head, ld_in, M, nf, out: Planes, ld):
+    _lib.check(_lib.load().qb_istft_pre(_p(head), ld_in, M, nf, _p(out.hi), _p(out.lo), ld, _stream()))
+
+
+def istft_ola(frames, window, B, F, n_fft, wav):
+    _lib.check(_lib.load().qb_istft_ola(_p(frames), _p(window), B, F, n_fft, _p(wav), _stream()))
+
+
+def attention(qkv, B, T, heads, rope_cos, rope_sin, out: Planes):
+    _lib.check(_lib.load().qb_attention(_p(qkv), B, T, heads, _p(rope_cos), _p(rope_sin), _p(out.hi), _p(out.lo),
+                                        _stream()))
+
+
+def lstm_workspace_bytes(B, H):
+    return int(_lib.load().qb_lstm_workspace_bytes(B, H))
+
+
+def lstm(xp, whh: Planes, B, T, H, out: Planes, workspace):
+    _lib.check(_lib.load().qb_lstm(_p(xp), _p(whh.hi), None, B, T, H, _p(out.hi), _p(out.lo), _p(workspace), _stream()))
+
+
+def rvq_workspace_bytes(M, D, K):
+    return int(_lib.load().qb_rvq_workspace_bytes(M, D, K))
+
+
+def rvq_encode(x, codebooks, cb: Planes, neg_half_e2, e2max, M, D, K, nq, idx, quantized, workspace):
+    _lib.check(_lib.load().qb_rvq_encode(_p(x), _p(codebooks), _p(cb.hi), _p(cb.lo), _p(neg_half_e2), float(e2max), M, D,
+                                         K, nq, _p(idx), _p(quantized), _p(workspace), _stream()))
+
+
+def rvq_decode(idx, codebooks, M, D, K, nq, out, out_ld, col_off):
+    _lib.check(_lib.load().qb_rvq_decode(_p(idx), _p(codebooks), M, D, K, nq, _p(out), out_ld, col_off, _stream()))
+
+
+def launch_count() -> int:
+    return int(_lib.load().qb_launch_count())
+
+
+def launch_count_reset():
+    _lib.load().qb_launch_count_reset()
