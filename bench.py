@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py - H-Codec-2.0 encode + RVQ + decode throughput on B200 (BASELINE.json configs[1]).
+
+A "step" = one pass of the hot path (Codec.encode -> Codec.decode) over one synthetic batch of
+B=64 clips x 10 s at the shipped 48 kHz configuration (480 000 samples / clip, 125 tokens / stream),
+seeded random weights of the shipped architecture (large_12.5hz_config.yaml).  No pretrained
+weights / datasets exist offline, hence `data: synthetic`.
+
+  python bench.py --gpus 1 --steps 5 --warmup 3            # our arm (CUDA kernels via the C ABI)
+  python bench.py --impl reference --steps 2 --warmup 1     # the reference's CPU path (oracle port)
+  torchrun ... bench.py --gpus N ...                        # one rank per GPU, weak scaling
+
+Prints ONE JSON line (see README / DESIGN.md "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "hcodec2_encode_rvq_decode_samples_per_s"
+UNIT = "samples/s"
+# algorithmic FLOPs per 50 Hz frame (multiply-add = 2), encoder+semantic+RVQ+decoder
+FLOP_PER_FRAME = 2245.8e6
+
+H2_FULL = dict(
+    sampling_rate=48000,
+    encoder_config=dict(dim=1536, intermediate_dim=4608, dimension=512, n_fft=1920, hop_length=960,
+                        convnext_layers=24, transformer_layers=2, target_frame_rate=12.5, causal=False),
+    decoder_config=dict(input_channels=1024, dim=1536, intermediate_dim=4608, convnext_layers=32, n_fft=1920,
+                        hop_length=960, transformer_layers=2, target_frame_rate=12.5, causal=False),
+    quantizer_config=dict(dim=512, codebook_size=1024, num_quantizers=16, decay=0.99, kmeans_init=True,
+                          kmeans_iters=50, quantize_dropout=False),
+    semantic_encoder_config=dict(input_channels=768, encode_channels=1536, out_channels=512,
+                                 channel_ratios=[1, 1, 1], strides=[2, 1, 2]),
+    semantic_decoder_config=dict(code_dim=512, output_channels=768, decode_channels=1536,
+                                 channel_ratios=[1, 1, 1], strides=[2, 1, 2]),
+)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sus=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+def random_init_(model, seed: int):
+    """Seeded random weights of the shipped architecture, generated on the module's device."""
+    dev = next(model.parameters()).device
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if "rnn." in name:
+                H = p.shape[-1] if p.dim() == 2 else p.shape[0] // 4
+                p.copy_((torch.rand(p.shape, generator=g, device=dev) * 2 - 1) / H ** 0.5)
+            elif name.endswith("gamma"):
+                n_layers = 24 if name.startswith("encoder.") else 32
+                p.copy_((1.0 / n_layers) * (1 + 0.2 * torch.randn(p.shape, generator=g, device=dev)))
+            elif p.dim() >= 2:
+                fan = p[0].numel()
+                p.copy_(torch.randn(p.shape, generator=g, device=dev) * fan ** -0.5)
+            elif "norm" in name and name.endswith("weight") or name.endswith("prior_net.7.weight"):
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g, device=dev))
+            else:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g, device=dev))
+        for q in (model.quantizer, model.semantic_quantizer):
+            cb = torch.stack([torch.randn(q.codebook_size, q.dim, generator=g, device=dev) * 0.35 * 0.85 ** i
+                              for i in range(q.num_quantizers)], 0)
+            q.set_codebooks(cb)
+    model._w = None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+_BEST_THREADS = None
+
+
+def _best_threads(sd, cfg):
+    """Pick the host thread count that makes the reference's CPU path fastest (short calibration on a
+    0.8 s clip): on a many-core shared host `all cores` is often far slower than a moderate count."""
+    global _BEST_THREADS
+    if _BEST_THREADS is None:
+        from oracle import hcodec2
+        try:
+            avail = len(os.sched_getaffinity(0))
+        except Exception:
+            avail = os.cpu_count() or 1
+        g = torch.Generator().manual_seed(3)
+        wav = 0.1 * torch.randn(1, 38400, generator=g)
+        feat = torch.randn(1, 768, 40, generator=g)
+        best = (1e30, 1)
+        for n in sorted({min(avail, c) for c in (8, 16, 32, 64, avail)}):
+            torch.set_num_threads(n)
+            hcodec2.codec_encode(sd, cfg, wav, feat)   # warm
+            t0 = time.perf_counter()
+            hcodec2.codec_encode(sd, cfg, wav, feat)
+            dt = time.perf_counter() - t0
+            if dt < best[0]:
+                best = (dt, n)
+        _BEST_THREADS = best[1]
+    return _BEST_THREADS
+
+
+def cpu_baseline(model_sd_cpu, cfg, seconds, clips):
+    """The reference's own PyTorch CPU path (oracle port, pinned bit-exact against the reference
+    modules) on this box's host cores, on a bounded sample of the same workload."""
+    from oracle import hcodec2
+    torch.set_num_threads(_best_threads(model_sd_cpu, cfg))
+    T = int(seconds * cfg["sampling_rate"])
+    g = torch.Generator().manual_seed(7)
+    wav = 0.1 * torch.randn(clips, T, generator=g)
+    f = torch.randn(clips, 768, T // 960, generator=g)
+    feat = torch.sign(f) * f.abs() ** 0.3
+    t0 = time.perf_counter()
+    ac, sc = hcodec2.codec_encode(model_sd_cpu, cfg, wav, feat)
+    hcodec2.codec_decode(model_sd_cpu, cfg, ac, sc)
+    dt = time.perf_counter() - t0
+    return clips * T / dt, dt
+
+
+def run_reference(args, cfg):
+    """--impl reference: the CPU path alone, same metric / config (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import weights
+    torch.manual_seed(0)
+    sd = weights.make_h2_state_dict(cfg, 0)
+    clips = args.ref_clips
+    times = []
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu_baseline(sd, cfg, args.seconds, clips)
+        if i >= args.warmup:
+            times.append(dt)
+    T = int(args.seconds * cfg["sampling_rate"])
+    ms = 1e3 * sum(times) / len(times)
+    value = clips * T / (ms / 1e3)
+    cores = _BEST_THREADS
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload=f"HCodec-2.0 (48 kHz shipped config) {args.seconds:g} s clips, encode+RVQ+decode",
+                            batch_per_step=clips, samples_per_clip=T, cpu_threads=cores),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
+                                  sample=f"{clips} clip(s) x {args.seconds:g} s per step, oracle port of the reference "
+                                         f"(pinned bit-exact against the reference modules), torch CPU fp32"),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--precision", default="mixed")
+    ap.add_argument("--ref-clips", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling aid: W warm-up + K steps only, no e2e/roofline/cpu legs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    cfg = H2_FULL
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+
+    from unified_audio_b200 import ops
+    from unified_audio_b200.codec import Codec
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    peaks = load_peaks()
+
+    model = Codec(cfg["encoder_config"], cfg["decoder_config"], cfg["quantizer_config"],
+                  cfg["semantic_encoder_config"], cfg["semantic_decoder_config"], precision=args.precision).to(dev)
+    random_init_(model, 1234)
+    B, T = args.batch, int(args.seconds * cfg["sampling_rate"])
+    T -= T % 3840
+    F_ = T // 960
+    g = torch.Generator().manual_seed(2000 + rank)
+    wav_h = (0.1 * torch.randn(B, T, generator=g)).pin_memory()
+    f = torch.randn(B, 768, F_, generator=g)
+    feat_h = (torch.sign(f) * f.abs() ** 0.3).pin_memory()
+    wav_d, feat_d = wav_h.to(dev), feat_h.to(dev)
+
+    def step_device():
+        ac, sc = model.encode(wav_d, feat_d)
+        rec = model.decode(ac, sc)
+        if dist is not None:   # the path's single exchange: gather the int64 tokens
+            out = [torch.empty_like(ac) for _ in range(world)]
+            dist.all_gather(out, ac)
+        return ac, sc, rec
+
+    codes_h = torch.empty(2, B, 16, T // 3840, dtype=torch.int64).pin_memory()
+    rec_h = torch.empty(B, T).pin_memory()
+
+    def step_e2e():
+        w = wav_h.to(dev, non_blocking=True)
+        ft = feat_h.to(dev, non_blocking=True)
+        ac, sc = model.encode(w, ft)
+        rec = model.decode(ac, sc)
+        codes_h[0].copy_(ac, non_blocking=True)
+        codes_h[1].copy_(sc, non_blocking=True)
+        rec_h.copy_(rec, non_blocking=True)
+        return rec
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        barrier()
+        ev[0].record()
+        for i in range(steps):
+            fn()
+            ev[i + 1].record()
+        barrier()
+        total_ms = ev[0].elapsed_time(ev[-1])
+        if dist is not None:
+            t = torch.tensor([total_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t)
+        return total_ms / steps
+
+    if args.quick:
+        for _ in range(args.warmup):
+            step_device()
+        ms = timed(step_device, args.steps)
+        if rank == 0:
+            print(json.dumps(dict(quick=True, ms_per_step=ms, value=world * B * T / (ms * 1e-3))))
+        return
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.launch_count_reset()
+    ms = timed(step_device, args.steps)
+    launches = ops.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # ---- roofline of the dominant kernel: the ConvNeXt pointwise GEMM (tcgen05), timed alone
+    M, C, I = B * F_, 1536, 4608
+    blk = model._prepare()["enc"]["convnext"][0]
+    t1 = model._planes("cnx_t1", (M, C), model.policy["convnext"])
+    hid = model._planes("cnx_hid", (M, I), model.policy["convnext"])
+    reps = 10
+    for _ in range(3):
+        model._linear(t1, blk["w1"], I, M, C, bias=blk["b1"], act=ops.ACT_GELU, out_planes=hid, out_planes_map=(I, M, 0))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        model._linear(t1, blk["w1"], I, M, C, bias=blk["b1"], act=ops.ACT_GELU, out_planes=hid, out_planes_map=(I, M, 0))
+    e1.record()
+    torch.cuda.synchronize()
+    gemm_ms = e0.elapsed_time(e1) / reps
+    gemm_tf = 2.0 * M * I * C / (gemm_ms * 1e-3) / 1e12
+
+    if rank != 0:
+        return
+    samples = world * B * T
+    value = samples / (ms * 1e-3)
+    path_tf = world * B * F_ * FLOP_PER_FRAME / (ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    line = dict(
+        metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+        ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16x3/f16 tensor-core, f32 accumulate",
+        data="synthetic",
+        config=dict(workload="HCodec-2.0 batch=64 x 10 s (48 kHz shipped config, 480000 samples/clip) encode+RVQ+decode",
+                    batch_per_gpu=B, samples_per_clip=T, tokens_per_stream=T // 3840, precision_policy=args.precision,
+                    l2="working set per step (~3 GB activations + 4.6 GB weights) exceeds the 126 MB L2; no flush needed",
+                    parallelism=f"dp{world} (clips sharded, one NCCL all_gather of tokens)"),
+        e2e=dict(value=samples / (ms_e2e * 1e-3), unit=UNIT, ms_per_step=ms_e2e,
+                 h2d_bytes_per_step=int(wav_h.numel() * 4 + feat_h.numel() * 4),
+                 d2h_bytes_per_step=int(codes_h.numel() * 8 + rec_h.numel() * 4)),
+        gpu_launches=int(launches),
+        clocks=clocks,
+        roofline=dict(bound="tensor", achieved=gemm_tf, peak=peaks["tf_burst"], unit="TFLOP/s", frac=gemm_tf / peaks["tf_burst"],
+                      traffic=traffic, kernel="gemm_tc_kernel<256,1,4> ConvNeXt pwconv1 [32000x4608x1536] fp16, timed alone",
+                      peak_source=f"{peaks['src']} dense bf16 burst (fp16 shares the pipe)",
+                      path_algorithmic_tflops=path_tf, path_frac_of_sustained=path_tf / peaks["tf_sus"]),
+    )
+    if not args.no_cpu_baseline:
+        sd_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        v, dt = cpu_baseline(sd_cpu, cfg, args.seconds, 1)
+        line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=_BEST_THREADS, kind="port",
+                                    sample=f"1 clip x {args.seconds:g} s encode+RVQ+decode ({dt:.1f} s), oracle port of "
+                                           "the reference's PyTorch CPU path, same weights")
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -143,6 +143,12 @@ int qb_istft_ola(const float* frames, const float* window, int64_t B, int64_t F,
  * (encoder_modules/transformer.py:134-182).  qkv [B,T,3*H*D] fp32 (q|k|v), D = 64.  Output planes. */
 int qb_attention(const float* qkv, int64_t B, int64_t T, int32_t heads, const float* rope_cos,
                  const float* rope_sin, qb_half* out_hi, qb_half* out_lo, void* stream);
+/* Same attention on the tensor cores (mma.sync m16n8k16): q,k,v rounded to fp16 after RoPE, fp32
+ * softmax / accumulation - the single-pass fp16 precision class.  workspace:
+ * qb_attention_tc_workspace_bytes(B,T,heads). */
+int64_t qb_attention_tc_workspace_bytes(int64_t B, int64_t T, int32_t heads);
+int qb_attention_tc(const float* qkv, int64_t B, int64_t T, int32_t heads, const float* rope_cos,
+                    const float* rope_sin, qb_half* out_hi, qb_half* out_lo, void* workspace, void* stream);
 /* Single-layer LSTM recurrence (encoder_modules/transformer.py:115,133): xp [B,T,4H] fp32 already
  * holds x W_ih^T + b_ih + b_hh; w_hh planes [4H, H]; output h planes [B,T,H].
  * workspace: qb_lstm_workspace_bytes(B,H). */

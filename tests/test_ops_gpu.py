@@ -175,6 +175,13 @@ def test_attention(lib):
     e = relerr(planes_ref(out), ref)
     print("attention relerr", e)
     assert e < 1e-5
+    out2 = ops.Planes.zeros((B, T, H * D), True, DEV)
+    ws = torch.zeros(ops.attention_tc_workspace_bytes(B, T, H), dtype=torch.uint8, device=DEV)
+    ops.attention_tc(qkv, B, T, H, cos, sin, out2, ws)
+    torch.cuda.synchronize()
+    e2 = relerr(planes_ref(out2), ref)
+    print("attention_tc (fp16 operands) relerr", e2)
+    assert e2 < 3e-3
 
 
 @pytest.mark.parametrize("B,T,H", [(2, 9, 256), (3, 20, 512), (5, 12, 1536)])

@@ -51,6 +51,8 @@ SIGNATURES = {
     "qb_istft_pre": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _vp]),
     "qb_istft_ola": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp]),
     "qb_attention": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "qb_attention_tc_workspace_bytes": (C.c_int64, [_i64, _i64, _i32]),
+    "qb_attention_tc": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qb_lstm_workspace_bytes": (C.c_int64, [_i64, _i64]),
     "qb_lstm": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "qb_rvq_workspace_bytes": (C.c_int64, [_i64, _i32, _i32]),

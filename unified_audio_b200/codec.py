@@ -266,13 +266,17 @@ class Codec(nn.Module):
         qkv = self._buf("tf_qkv", (M, 3 * C))
         ws = self._buf("lstm_ws", (ops.lstm_workspace_bytes(B, C),), torch.uint8)
         cos, sin = self._rope(F)
+        att_ws = None if pa else self._buf("att_ws", (ops.attention_tc_workspace_bytes(B, F, heads),), torch.uint8)
         xm = rowmap(x, C, M, 0)
         for L in layers:
             ops.rmsnorm(x, L["in_w"], M, C, t_a)
             self._linear(t_a, L["wih"], 4 * C, M, C, bias=L["b_ih"], out_f32=rowmap(xp, 4 * C, M, 0))
             ops.lstm(xp, L["whh"], B, F, C, t_b, ws)
             self._linear(t_b, L["wqkv"], 3 * C, M, C, bias=L["bqkv"], out_f32=rowmap(qkv, 3 * C, M, 0))
-            ops.attention(qkv, B, F, heads, cos, sin, t_a)
+            if pa:   # split-precision policy: fp32 SIMT attention
+                ops.attention(qkv, B, F, heads, cos, sin, t_a)
+            else:    # single-pass fp16 policy: tensor-core flash attention
+                ops.attention_tc(qkv, B, F, heads, cos, sin, t_a, att_ws)
             self._linear(t_a, L["wo"], C, M, C, residual=xm, out_f32=xm)
             ops.rmsnorm(x, L["post_w"], M, C, t_m)
             self._linear(t_m, L["w13"], 2 * I, M, C, act=ACT_SWIGLU, out_planes=hid, out_planes_map=(I, M, 0))

@@ -126,6 +126,108 @@ __global__ void dwconv7_ln_kernel(const float* __restrict__ x, const float* __re
   for (int c = lane; c < C; c += 32) store_planes(hi, lo, row * C + c, (y[c] - mean) * rstd * ln_w[c] + ln_b[c]);
 }
 
+// v2: block = (TT consecutive frames of one clip) x (all channels); one thread owns 4 channels
+// (float4 along C => fully coalesced 16 B accesses) and slides a 7-row register window over time, so
+// each input row is read once per block (halo re-reads hit L2).  LayerNorm statistics for the TT rows
+// are block-reduced together (two-pass: mean, then centred variance).
+template <int TT>
+__global__ void __launch_bounds__(512)
+dwconv7_ln_v2_kernel(const float4* __restrict__ x, const float* __restrict__ dw_w, const float4* __restrict__ dw_b,
+                     const float4* __restrict__ ln_w, const float4* __restrict__ ln_b, int T, int C4,
+                     __half* __restrict__ hi, __half* __restrict__ lo) {
+  __shared__ float red[16][TT];
+  __shared__ float tot[TT];
+  const int b = blockIdx.y, t0 = blockIdx.x * TT, c4 = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float w[28];
+  {
+    const float4* wp = reinterpret_cast<const float4*>(dw_w + (size_t)c4 * 28);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      float4 v = wp[i];
+      w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+    }
+  }
+  const float4 bias = dw_b[c4];
+  const float4* xb = x + (size_t)b * T * C4 + c4;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 win[7];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int tt = t0 - 3 + j;
+    win[j] = (tt >= 0 && tt < T) ? xb[(size_t)tt * C4] : zero;
+  }
+  float4 y[TT];
+#pragma unroll
+  for (int i = 0; i < TT; ++i) {
+    const int tt = t0 + i + 3;
+    win[6] = (tt < T) ? xb[(size_t)tt * C4] : zero;
+    float4 a = bias;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      a.x = fmaf(w[j], win[j].x, a.x);
+      a.y = fmaf(w[7 + j], win[j].y, a.y);
+      a.z = fmaf(w[14 + j], win[j].z, a.z);
+      a.w = fmaf(w[21 + j], win[j].w, a.w);
+    }
+    y[i] = a;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
+  }
+  const float invC = 1.f / (4.f * C4);
+  float mean[TT], rstd[TT];
+  // pass 1: means
+#pragma unroll
+  for (int i = 0; i < TT; ++i) {
+    float s = warp_sum(y[i].x + y[i].y + y[i].z + y[i].w);
+    if (lane == 0) red[warp][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < TT) {
+    float s = 0.f;
+    for (int wv = 0; wv < nwarps; ++wv) s += red[wv][threadIdx.x];
+    tot[threadIdx.x] = s * invC;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < TT; ++i) mean[i] = tot[i];
+  __syncthreads();
+  // pass 2: centred variance
+#pragma unroll
+  for (int i = 0; i < TT; ++i) {
+    const float dx = y[i].x - mean[i], dy = y[i].y - mean[i], dz = y[i].z - mean[i], dw = y[i].w - mean[i];
+    float s = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw);
+    if (lane == 0) red[warp][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < TT) {
+    float s = 0.f;
+    for (int wv = 0; wv < nwarps; ++wv) s += red[wv][threadIdx.x];
+    tot[threadIdx.x] = rsqrtf(s * invC + 1e-6f);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < TT; ++i) rstd[i] = tot[i];
+  const float4 lw = ln_w[c4], lb = ln_b[c4];
+#pragma unroll
+  for (int i = 0; i < TT; ++i) {
+    const int t = t0 + i;
+    if (t < T) {
+      const float v0 = (y[i].x - mean[i]) * rstd[i] * lw.x + lb.x, v1 = (y[i].y - mean[i]) * rstd[i] * lw.y + lb.y;
+      const float v2 = (y[i].z - mean[i]) * rstd[i] * lw.z + lb.z, v3 = (y[i].w - mean[i]) * rstd[i] * lw.w + lb.w;
+      __half h0, h1, h2, h3, l0, l1, l2, l3;
+      split_f16(v0, h0, l0); split_f16(v1, h1, l1); split_f16(v2, h2, l2); split_f16(v3, h3, l3);
+      const size_t o = ((size_t)b * T + t) * C4 + c4;
+      __half2 hh[2] = {__halves2half2(h0, h1), __halves2half2(h2, h3)};
+      reinterpret_cast<uint2*>(hi)[o] = *reinterpret_cast<uint2*>(hh);
+      if (lo) {
+        __half2 ll[2] = {__halves2half2(l0, l1), __halves2half2(l2, l3)};
+        reinterpret_cast<uint2*>(lo)[o] = *reinterpret_cast<uint2*>(ll);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ GroupNorm
 __global__ void groupnorm_stats_kernel(const float* __restrict__ x, int T, int C, int G, float eps,
                                        float* __restrict__ stats) {
@@ -291,6 +393,14 @@ extern "C" int qb_dwconv7_ln(const float* x, const float* dw_w, const float* dw_
                              const float* ln_b, int64_t B, int64_t T, int64_t C, qb_half* hi, qb_half* lo,
                              void* stream) {
   QB_REQUIRE(x && dw_w && dw_b && ln_w && ln_b && hi, "dwconv7_ln: bad args");
+  if (C % 128 == 0 && C / 4 <= 512) {
+    constexpr int TT = 8;
+    dim3 grid((unsigned)ceil_div(T, TT), (unsigned)B);
+    dwconv7_ln_v2_kernel<TT><<<grid, (unsigned)(C / 4), 0, (cudaStream_t)stream>>>(
+        (const float4*)x, dw_w, (const float4*)dw_b, (const float4*)ln_w, (const float4*)ln_b, (int)T, (int)(C / 4),
+        (__half*)hi, (__half*)lo);
+    QB_LAUNCH_END();
+  }
   const int warps = 8;
   const size_t smem = (size_t)warps * C * sizeof(float);
   QB_REQUIRE(smem <= 200 * 1024, "dwconv7_ln: C too large");

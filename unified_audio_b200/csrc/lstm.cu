@@ -55,22 +55,23 @@ lstm_kernel(const float* __restrict__ xp, const __half* __restrict__ whh, int B,
   const int u0 = blockIdx.x * U;
   const int G = gridDim.x;
 
-  // one-time: W_hh slice -> smem, K order permuted inside every 16-block:
-  // logical 32-bit word w (0..7) <- memory word (w<4 ? 2w : 2(w-4)+1)
+  // one-time: W_hh slice -> smem, K order permuted inside every 32-block so that the 8 consecutive
+  // memory halves a thread fetches with one 128-bit load are its B-fragment registers of two k16 steps:
+  // logical 32-bit word wl (0..15) of a block <- memory word 4*(wl&3) + ((wl>>2)&1) + 2*(wl>>3)
   const int wpr = H / 2;  // 32-bit words per row
   for (int idx = tid; idx < ROWS * wpr; idx += LSTM_THREADS) {
     const int r = idx / wpr, wl = idx - r * wpr;
-    const int kb = wl >> 3, w8 = wl & 7;
-    const int memw = (w8 < 4) ? 2 * w8 : 2 * (w8 - 4) + 1;
+    const int kb = wl >> 4, w16 = wl & 15;
+    const int memw = 4 * (w16 & 3) + ((w16 >> 2) & 1) + 2 * (w16 >> 3);
     const int g = r / U, j = r - g * U;
     const uint32_t* src = reinterpret_cast<const uint32_t*>(whh + ((long long)g * H + u0 + j) * H);
-    reinterpret_cast<uint32_t*>(Wsm + (size_t)r * pitch)[wl] = src[kb * 8 + memw];
+    reinterpret_cast<uint32_t*>(Wsm + (size_t)r * pitch)[wl] = src[kb * 16 + memw];
   }
   for (int i = tid; i < Bp * U; i += LSTM_THREADS) cs[i] = 0.f;
   __syncthreads();
 
   const int nh = warp & 1, kq = warp >> 1;
-  const int kb_per_q = H / 64;  // 16-wide K blocks per quarter
+  const int kb32_per_q = H / 128;  // 32-wide K blocks per K quarter
   const int n_chunks = Bp / LSTM_NB;
 
   for (int t = 0; t < T; ++t) {
@@ -109,26 +110,40 @@ lstm_kernel(const float* __restrict__ xp, const __half* __restrict__ whh, int B,
 #pragma unroll
           for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
       if (t > 0) {
-        const __half* hb = hprev + (size_t)(nb0 + nh * 32 + (lane >> 2)) * H + (lane & 3) * 4;
-        const int kb_end = (kq + 1) * kb_per_q;
-        for (int kb0 = kq * kb_per_q; kb0 < kb_end; kb0 += 8) {
-          uint2 bf[8][4];
+        const __half* hb = hprev + (size_t)(nb0 + nh * 32 + (lane >> 2)) * H + (lane & 3) * 8;
+        const int kb_beg = kq * kb32_per_q, kb_end = kb_beg + kb32_per_q;   // 32-wide K blocks of this quarter
+        for (int g0 = kb_beg; g0 < kb_end; g0 += 12) {
+          uint4 bf[2][4][4];
+          auto load_group = [&](int buf, int kb0) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
+            for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
-              bf[kk][nt] = (kb0 + kk < kb_end)
-                               ? __ldcg(reinterpret_cast<const uint2*>(hb + (size_t)nt * 8 * H + (kb0 + kk) * 16))
-                               : make_uint2(0u, 0u);
+              for (int nt = 0; nt < 4; ++nt)
+                bf[buf][kk][nt] = (kb0 + kk < kb_end)
+                                      ? __ldcg(reinterpret_cast<const uint4*>(hb + (size_t)nt * 8 * H + (kb0 + kk) * 32))
+                                      : make_uint4(0u, 0u, 0u, 0u);
+          };
+          load_group(0, g0);
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            if (kb0 + kk < kb_end) {
+          for (int gi = 0; gi < 3; ++gi) {
+            const int kb0 = g0 + gi * 4;
+            if (gi + 1 < 3 && kb0 + 4 < kb_end) load_group((gi + 1) & 1, kb0 + 4);
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                uint32_t a[4];
-                ldmatrix_x4(a, Wsm + (size_t)(mt * 16 + (lane & 15)) * pitch + (kb0 + kk) * 16 + (lane >> 4) * 8);
+            for (int kk = 0; kk < 4; ++kk) {
+              if (kb0 + kk < kb_end) {
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) mma_16816(acc[mt][nt], a, bf[kk][nt].x, bf[kk][nt].y);
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                  for (int mt = 0; mt < MT; ++mt) {
+                    uint32_t a[4];
+                    ldmatrix_x4(a, Wsm + (size_t)(mt * 16 + (lane & 15)) * pitch + (kb0 + kk) * 32 + half * 16 + (lane >> 4) * 8);
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                      const uint4 v = bf[gi & 1][kk][nt];
+                      mma_16816(acc[mt][nt], a, half ? v.z : v.x, half ? v.w : v.y);
+                    }
+                  }
+                }
               }
             }
           }
@@ -205,7 +220,7 @@ extern "C" int qb_lstm(const float* xp, const qb_half* whh_hi, const qb_half* wh
   cudaStream_t st = (cudaStream_t)stream;
   QB_REQUIRE(xp && whh_hi && out_hi && workspace, "lstm: bad args");
   QB_REQUIRE(whh_lo == nullptr, "lstm: split-precision recurrent weights are not supported (single-pass fp16 policy)");
-  QB_REQUIRE(H % 64 == 0, "lstm: H must be a multiple of 64");
+  QB_REQUIRE(H % 128 == 0, "lstm: H must be a multiple of 128");
   int dev = 0, sms = 0;
   QB_CHECK_CUDA(cudaGetDevice(&dev));
   QB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

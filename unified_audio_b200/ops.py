@@ -145,6 +145,15 @@ def attention(qkv, B, T, heads, rope_cos, rope_sin, out: Planes):
                                         _stream()))
 
 
+def attention_tc_workspace_bytes(B, T, heads):
+    return int(_lib.load().qb_attention_tc_workspace_bytes(B, T, heads))
+
+
+def attention_tc(qkv, B, T, heads, rope_cos, rope_sin, out: Planes, workspace):
+    _lib.check(_lib.load().qb_attention_tc(_p(qkv), B, T, heads, _p(rope_cos), _p(rope_sin), _p(out.hi), _p(out.lo),
+                                           _p(workspace), _stream()))
+
+
 def lstm_workspace_bytes(B, H):
     return int(_lib.load().qb_lstm_workspace_bytes(B, H))
 
