@@ -217,6 +217,7 @@ def main():
 
     from unified_audio_b200 import ops
     from unified_audio_b200.codec import Codec
+    from unified_audio_b200.parallel import gather_tokens
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -246,8 +247,7 @@ def main():
         ac, sc = model.encode(wav_d, feat_d)
         rec = model.decode(ac, sc)
         if dist is not None:   # the path's single exchange: gather the int64 tokens
-            out = [torch.empty_like(ac) for _ in range(world)]
-            dist.all_gather(out, ac)
+            gather_tokens(torch.stack([ac, sc], 1), world * B)
         return ac, sc, rec
 
     codes_h = torch.empty(2, B, 16, T // 3840, dtype=torch.int64).pin_memory()

@@ -6,3 +6,6 @@ Public surface mirrors the reference (alibaba/unified-audio):
 Kernels live in csrc/ behind the C ABI of include/quark_b200.h (lib/libquark_b200.so).
 """
 __version__ = "0.1.0"
+
+from .codec import Codec  # noqa: E402,F401
+from .rvq import ResidualVQ  # noqa: E402,F401

@@ -3,10 +3,10 @@
 //
 // Tile: 128 (rows) x BN (cols) x 64 (K) per pipeline stage, fp16 planes K-major in shared memory
 // with the 128-byte TMA/UMMA swizzle; accumulators live in TMEM (double buffered: 2 x BN columns)
-// so the epilogue of tile i overlaps the MMAs of tile i+1.  Warp roles (320 threads):
-//   warps 0-7  epilogue   (TMEM -> registers -> bias/act/gamma/residual -> global)
-//   warp  8    TMA producer (one lane)
-//   warp  9    TMEM allocator + MMA issuer (one lane)
+// so the epilogue of tile i overlaps the MMAs of tile i+1.  Warp roles (576 threads):
+//   warps 0-15 epilogue   (TMEM -> registers -> bias/act/gamma/residual -> global)
+//   warp  16   TMA producer (one lane)
+//   warp  17   TMEM allocator + MMA issuer (one lane)
 // Convolutions are expressed as `taps` shifted K-panels over a zero-padded channel-last buffer:
 // the A tensor map views the buffer as [batch][rows/stride][stride*C], so tap t of output row m is
 // the box at (x = (t % stride)*C + c, y = m + t / stride) - TMA-staged im2col without an im2col
@@ -51,7 +51,7 @@ struct GemmParams {
 };
 
 __device__ __forceinline__ float apply_act(int act, float v) {
-  if (act == QB_ACT_GELU) return gelu_erf(v);
+  if (act == QB_ACT_GELU) return gelu_fast(v);
   if (act == QB_ACT_ELU) return elu_f(v);
   return v;
 }
@@ -78,9 +78,18 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int b, int m
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
   if (p.bias) {
+    if (n_base + 32 <= p.N && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
+      const float4* bp = reinterpret_cast<const float4*>(p.bias + n_base);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (n_base + j < p.N) v[j] += __ldg(p.bias + n_base + j);
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(bp + j);
+        v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n_base + j < p.N) v[j] += __ldg(p.bias + n_base + j);
+    }
   }
   int ncols = 32, n_out = n_base, N_out = p.N;
   if (p.act == QB_ACT_SWIGLU) {
@@ -103,9 +112,19 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int b, int m
     return;
   }
   if (p.gamma) {
+    if ((reinterpret_cast<uintptr_t>(p.gamma) & 15) == 0) {
+      const float4* gp = reinterpret_cast<const float4*>(p.gamma + n_out);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < ncols) v[j] *= __ldg(p.gamma + n_out + j);
+      for (int j = 0; j < 8; ++j)
+        if (4 * j < ncols) {
+          const float4 t = __ldg(gp + j);
+          v[4 * j] *= t.x; v[4 * j + 1] *= t.y; v[4 * j + 2] *= t.z; v[4 * j + 3] *= t.w;
+        }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) v[j] *= __ldg(p.gamma + n_out + j);
+    }
   }
   if (p.res.ptr) {
     const float4* rp = (const float4*)((const float*)p.res.ptr + ((long long)b * p.res.rpb + p.res.off + m) * p.res.ld + n_out);
@@ -130,15 +149,17 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int b, int m
     for (int j = 0; j < 4; ++j)
       if (8 * j < ncols) {
         __half2 h2[4], l2[4];
+        const __half2 hmax = __float2half2_rn(65504.f), hmin = __float2half2_rn(-65504.f);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float u0 = v[8 * j + 2 * e], u1 = v[8 * j + 2 * e + 1];
           if (p.act2 == QB_ACT_ELU) { u0 = elu_f(u0); u1 = elu_f(u1); }
-          __half a, b2, c, d;
-          split_f16(u0, a, c);
-          split_f16(u1, b2, d);
-          h2[e] = __halves2half2(a, b2);
-          l2[e] = __halves2half2(c, d);
+          const __half2 hh = __hmax2(__hmin2(__floats2half2_rn(u0, u1), hmax), hmin);   // saturate, no inf
+          h2[e] = hh;
+          if (lp) {
+            const float2 back = __half22float2(hh);
+            l2[e] = __floats2half2_rn(u0 - back.x, u1 - back.y);
+          }
         }
         hp[j] = *reinterpret_cast<uint4*>(h2);
         if (lp) lp[j] = *reinterpret_cast<uint4*>(l2);
@@ -150,8 +171,10 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
   return (uint8_t*)(((uintptr_t)p + 1023) & ~(uintptr_t)1023);
 }
 
+constexpr int GEMM_EPI_WARPS = 16, GEMM_THREADS = (GEMM_EPI_WARPS + 2) * 32;
+
 template <int BN, int NTERMS, int STAGES>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                const GemmParams p) {
@@ -173,11 +196,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], GEMM_EPI_WARPS); }
     fence_mbar_init();
   }
-  if (warp == 9) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
-  if (warp == 8 && lane == 0) {
+  if (warp == GEMM_EPI_WARPS + 1) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  if (warp == GEMM_EPI_WARPS && lane == 0) {
     prefetch_tmap(&tmA_hi); prefetch_tmap(&tmW_hi);
     if (NPL == 2) { prefetch_tmap(&tmA_lo); prefetch_tmap(&tmW_lo); }
   }
@@ -186,7 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == GEMM_EPI_WARPS) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -206,7 +229,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == GEMM_EPI_WARPS + 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(BM, BN);
       uint32_t stage = 0, phase = 0, it = 0;
@@ -238,6 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else {
+    constexpr int CPW = BN / (GEMM_EPI_WARPS / 4);   // accumulator columns per epilogue warp
     const int q = warp & 3, hc = warp >> 2;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -246,13 +270,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + hc * (BN / 2);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + hc * CPW;
 #pragma unroll 1
-      for (int c = 0; c < BN / 2; c += 32) {
+      for (int c = 0; c < CPW; c += 32) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + c, r);
         tmem_ld_wait();
-        epilogue_row32(p, b, m0 + q * 32 + lane, n0 + hc * (BN / 2) + c, r);
+        epilogue_row32(p, b, m0 + q * 32 + lane, n0 + hc * CPW + c, r);
       }
       tc_fence_before();
       __syncwarp();
@@ -261,7 +285,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == GEMM_EPI_WARPS + 1) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -397,7 +421,7 @@ static int launch_tc(const qb_gemm_desc* d, cudaStream_t st, int num_sms) {
     attr_set = true;
   }
   int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  kern<<<grid, 320, smem, st>>>(mA_hi, mA_lo, mW_hi, mW_lo, p);
+  kern<<<grid, GEMM_THREADS, smem, st>>>(mA_hi, mA_lo, mW_hi, mW_lo, p);
   g_launches++;
   QB_CHECK_CUDA(cudaGetLastError());
   return 0;
