@@ -104,9 +104,9 @@ int qb_bct_to_planes(const float* x, int64_t B, int64_t C, int64_t T, qb_half* h
 int qb_layernorm(const float* x, const float* w, const float* b, float eps, int64_t B, int64_t rows, int64_t C,
                  float* out_f32, qb_half* hi, qb_half* lo, int64_t ld, int64_t rows_per_batch, int64_t row_off,
                  void* stream);
-/* RMSNorm (encoder_modules/transformer.py:77-96) -> planes. */
-int qb_rmsnorm(const float* x, const float* w, float eps, int64_t rows, int64_t C, qb_half* hi, qb_half* lo,
-               void* stream);
+/* RMSNorm (encoder_modules/transformer.py:77-96; HF LlamaRMSNorm) -> fp32 and/or planes (any may be NULL). */
+int qb_rmsnorm(const float* x, const float* w, float eps, int64_t rows, int64_t C, float* out_f32, qb_half* hi,
+               qb_half* lo, void* stream);
 /* ConvNeXt front half: depthwise conv k=7 (zero pad 3) over time + LayerNorm(1e-6) -> planes
  * (vq/conv.py:201-204).  x [B, T, C] fp32; dw_w [C,7]; dw_b [C]. */
 int qb_dwconv7_ln(const float* x, const float* dw_w, const float* dw_b, const float* ln_w, const float* ln_b,
@@ -171,6 +171,35 @@ int qb_rvq_encode(const float* x, const float* codebooks, const qb_half* cb_hi, 
  * summed q = 0..nq-1 in fp32 (codec.py:94-95). */
 int qb_rvq_decode(const int64_t* idx, const float* codebooks, int64_t M, int32_t D, int32_t K, int32_t nq,
                   float* out, int64_t out_ld, int64_t col_off, void* stream);
+
+/* ---------------------------------------------------------------- UniSE AR-LM (decoder-only Llama-style LM)
+ * Reference: QuarkAudio-UniSE/model/llm/llm.py:150-228 (llm_forward over HF Llama decoder layers),
+ * llm_sft.py:93-195 (prefill + 33 + T cached greedy steps).  The prefill / teacher-forced forward runs its
+ * projections through qb_gemm; these entry points add the attention side and the KV-cache decode step. */
+/* qkv [B,L,3*H*64] fp32 -> RoPE at absolute positions pos0.., q scaled by 1/8 -> q32 [B,H,L,64]; K/V appended
+ * to the static fp32 cache [B,H,Lmax,64] at pos0.. */
+int qb_lm_qkv_prep(const float* qkv, int64_t B, int64_t L, int32_t heads, int32_t pos0, const float* rope_cos,
+                   const float* rope_sin, float* q32, float* k_cache, float* v_cache, int32_t Lmax, void* stream);
+/* causal flash attention over the cache: query t (absolute position pos0+t) sees keys 0..pos0+t; operands are
+ * split into fp16 hi/lo planes on the fly and multiplied as 3-term split MMAs (fp32-grade scores). */
+int qb_lm_flash_attn(const float* q32, const float* k_cache, const float* v_cache, int64_t B, int64_t L,
+                     int32_t heads, int32_t pos0, int32_t Lmax, qb_half* out_hi, qb_half* out_lo, void* stream);
+/* One decoder layer for ONE new token per sequence (B <= 32), fp32 weights streamed once:
+ * x [B,hidden] updated in place; K/V appended at *pos (device int, not modified here).
+ * wqkv = [q;k;v] rows [3*hidden, hidden]; scratch q_buf/attn_buf [B,hidden], mlp_buf [B,inter]. */
+int qb_lm_decode_layer(float* x, int64_t B, int32_t hidden, int32_t heads, int32_t inter, const float* in_norm,
+                       const float* wqkv, const float* wo, const float* post_norm, const float* wgate,
+                       const float* wup, const float* wdown, float* k_cache, float* v_cache, int32_t Lmax,
+                       const int32_t* pos, const float* rope_cos, const float* rope_sin, float* q_buf,
+                       float* attn_buf, float* mlp_buf, void* stream);
+/* Final RMSNorm + output head restricted to columns [range[0], range[1]) (device ints; llm_sft.py:148-153)
+ * + greedy arg-max (llm.py:286-287, do_sample=False) -> out_ids[b*out_stride + slot[0]]; x_next[b] =
+ * embedding[token]; then slot[0]++ and *pos++ (slot is int32[2], second word is scratch).
+ * part_val/part_idx: scratch [max_cols/16 * 32]. */
+int qb_lm_head_argmax(const float* x, int64_t B, int32_t hidden, const float* final_norm, const float* w_head,
+                      const int32_t* range, int32_t max_cols, const float* embedding, float* x_next,
+                      int64_t* out_ids, int32_t out_stride, int32_t* pos, int32_t* slot, float* part_val,
+                      int32_t* part_idx, void* stream);
 
 #ifdef __cplusplus
 }

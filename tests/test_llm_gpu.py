@@ -1,0 +1,99 @@
+"""GPU parity of unified_audio_b200.LLM_SFT against the LM oracle (pinned against transformers.LlamaModel)
+and the committed golden fixture tests/golden/lm_small.npz."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-3
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def build(cfg, seed, gain):
+    from oracle import llama
+    from unified_audio_b200.llm import LLM_SFT
+    sd = llama.make_lm_state_dict(cfg, seed, gain)
+    m = LLM_SFT(num_tasks=cfg["num_tasks"], task_map=cfg["task_map"], feats_dim=cfg["feats_dim"],
+                llm_base_config=cfg["llm_base_config"])
+    sd2 = dict(sd)
+    sd2["cond_input_layer.weight"] = torch.zeros(4, 4)        # dead conformer weights of a real checkpoint
+    m.load_state_dict(sd2, strict=True)
+    return m.cuda(), sd
+
+
+def compare_tokens(tag, got, want, margins, thr=1e-4):
+    """first differing step per sequence must be a numerically unsafe decision (tiny top-2 logit margin)"""
+    got, want = got.cpu(), want.cpu()
+    nbad = 0
+    for b in range(want.shape[0]):
+        diff = (got[b] != want[b]).nonzero()
+        if len(diff):
+            nbad += 1
+            t = int(diff[0])
+            print(f"[{tag}] seq {b}: first divergence at step {t}, oracle margin {float(margins[b, t]):.2e}")
+            assert float(margins[b, t]) < thr, "token differs although the oracle's decision margin is safe"
+    print(f"[{tag}] sequences with a differing token: {nbad}/{want.shape[0]}")
+    return nbad
+
+
+def test_lm_small_golden(lib):
+    z = np.load(os.path.join(GOLD, "lm_small.npz"))
+    meta = json.loads(str(z["meta"]))
+    cfg = meta["cfg"]
+    m, sd = build(cfg, meta["seed"], meta["gain"])
+    mix, enr = torch.from_numpy(z["mix"]).cuda(), torch.from_numpy(z["enroll"]).cuda()
+    gids, sids = torch.from_numpy(z["gids"]).cuda(), torch.from_numpy(z["sids"]).cuda()
+    loss, acc, logits = m(task_name="tse", enroll_mel=enr, enroll_feats=enr, mix_mel=mix, mix_feats=mix, global_ids=gids,
+                          semantic_ids=sids, return_logits=True)
+    torch.cuda.synchronize()
+    e = rel(logits, torch.from_numpy(z["logits"]))
+    print(f"teacher-forced logits rel {e:.2e}  loss {float(loss):.6f} vs {float(z['loss']):.6f}")
+    assert e < TOL and abs(float(loss) - float(z["loss"])) < 1e-3 * abs(float(z["loss"]))
+    margins = torch.from_numpy(z["gen_margins"])
+    for graph in (False, True):
+        gg, ss = m.generate("se", None, None, mix, mix, do_sample=False, use_cuda_graph=graph)
+        torch.cuda.synchronize()
+        allt = torch.cat([gg.cpu() , torch.zeros(gg.shape[0], 1, dtype=torch.long), ss.cpu()], 1)
+        want = torch.cat([torch.from_numpy(z["gen_global"]), torch.zeros(gg.shape[0], 1, dtype=torch.long),
+                          torch.from_numpy(z["gen_semantic"])], 1)
+        margins2 = margins.clone(); margins2[:, 32] = 1.0      # the 33rd step's token is discarded by the reference
+        compare_tokens(f"small generate graph={graph}", allt, want, margins2)
+
+
+def test_lm_full_config_vs_oracle(lib):
+    """Shipped UniSE LM (12 x 512, vocab 12291): prefill + cached decode hidden states, then greedy generation."""
+    from oracle import llama
+    cfg = llama.LM_FULL
+    m, sd = build(cfg, 7, 2.0)
+    g = torch.Generator().manual_seed(11)
+    B, T = 4, 24
+    x = torch.randn(B, 70, 512, generator=g)
+    ref_full, _ = llama.llm_forward(sd, cfg, x)
+    out = m.llm_forward(x[:, :66].cuda(), use_cache=True)
+    hs = [out.last_hidden_state]
+    cache = out.past_key_values
+    for i in range(66, 70):
+        o = m.llm_forward(x[:, i:i + 1].cuda(), past_key_values=cache, use_cache=True)
+        hs.append(o.last_hidden_state)
+    torch.cuda.synchronize()
+    got = torch.cat(hs, 1)
+    e_pre, e_dec = rel(got[:, :66], ref_full[:, :66]), rel(got[:, 66:], ref_full[:, 66:])
+    print(f"llm_forward: prefill rel {e_pre:.2e}  cached decode rel {e_dec:.2e}")
+    assert e_pre < TOL and e_dec < TOL
+    mix = torch.randn(B, T, 768, generator=g)
+    enr = torch.randn(B, 30, 768, generator=g)
+    og, os_, margins = llama.sft_generate(sd, cfg, "tse", enr, mix, T, return_margins=True)
+    gg, ss = m.generate("tse", enr.cuda(), enr.cuda(), mix.cuda(), mix.cuda(), do_sample=False)
+    torch.cuda.synchronize()
+    margins[:, 32] = 1.0
+    zero = torch.zeros(B, 1, dtype=torch.long)
+    compare_tokens("full generate", torch.cat([gg.cpu(), zero, ss.cpu()], 1), torch.cat([og, zero, os_], 1), margins)
+    print("min oracle margin", float(margins.min()))

@@ -41,7 +41,7 @@ SIGNATURES = {
     "qb_rows_to_planes": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _i64, _i64, _i64, _vp]),
     "qb_bct_to_planes": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp]),
     "qb_layernorm": (C.c_int, [_vp, _vp, _vp, _f32, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
-    "qb_rmsnorm": (C.c_int, [_vp, _vp, _f32, _i64, _i64, _vp, _vp, _vp]),
+    "qb_rmsnorm": (C.c_int, [_vp, _vp, _f32, _i64, _i64, _vp, _vp, _vp, _vp]),
     "qb_dwconv7_ln": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "qb_groupnorm_stats": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _f32, _vp, _vp]),
     "qb_groupnorm_apply": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _i64,
@@ -58,6 +58,11 @@ SIGNATURES = {
     "qb_rvq_workspace_bytes": (C.c_int64, [_i64, _i32, _i32]),
     "qb_rvq_encode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "qb_rvq_decode": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _i64, _vp]),
+    "qb_lm_qkv_prep": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "qb_lm_flash_attn": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "qb_lm_decode_layer": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp,
+                                      _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qb_lm_head_argmax": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -82,7 +82,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 }
 
 __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, float eps, long long rows, int C,
-                               __half* __restrict__ hi, __half* __restrict__ lo) {
+                               float* __restrict__ out, __half* __restrict__ hi, __half* __restrict__ lo) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -90,7 +90,11 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restr
   float q = 0.f;
   for (int c = lane; c < C; c += 32) q += xr[c] * xr[c];
   const float r = rsqrtf(warp_sum(q) / C + eps);
-  for (int c = lane; c < C; c += 32) store_planes(hi, lo, row * C + c, xr[c] * r * w[c]);
+  for (int c = lane; c < C; c += 32) {
+    const float v = xr[c] * r * w[c];
+    if (out) out[row * C + c] = v;
+    if (hi) store_planes(hi, lo, row * C + c, v);
+  }
 }
 
 // ------------------------------------------------------------------ ConvNeXt: dwconv k7 + LayerNorm
@@ -381,11 +385,11 @@ extern "C" int qb_layernorm(const float* x, const float* w, const float* b, floa
   QB_LAUNCH_END();
 }
 
-extern "C" int qb_rmsnorm(const float* x, const float* w, float eps, int64_t rows, int64_t C, qb_half* hi, qb_half* lo,
-                          void* stream) {
-  QB_REQUIRE(x && w && hi, "rmsnorm: bad args");
-  rmsnorm_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, w, eps, rows, (int)C, (__half*)hi,
-                                                                                 (__half*)lo);
+extern "C" int qb_rmsnorm(const float* x, const float* w, float eps, int64_t rows, int64_t C, float* out_f32, qb_half* hi,
+                          qb_half* lo, void* stream) {
+  QB_REQUIRE(x && w && (hi || out_f32), "rmsnorm: bad args");
+  rmsnorm_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, w, eps, rows, (int)C, out_f32,
+                                                                                 (__half*)hi, (__half*)lo);
   QB_LAUNCH_END();
 }
 

@@ -1,0 +1,602 @@
+// UniSE AR-LM kernels (reference: QuarkAudio-UniSE/model/llm/llm.py:150-228, llm_sft.py:93-195; HF Llama
+// decoder layers: RMSNorm(1e-6) -> q/k/v (no bias) -> RoPE -> causal attention -> o_proj -> +res ->
+// RMSNorm -> SwiGLU MLP -> +res).
+//
+// Prefill / teacher-forced forward (L > 1) runs on the tcgen05 GEMM (gemm.cu) plus the two kernels here:
+//   lm_qkv_prep   RoPE at absolute positions, 1/sqrt(d) folded into q, K/V appended to the static fp32 cache
+//   lm_flash_attn causal flash attention (mma.sync m16n8k16, 3-term fp16 split of Q/K/P/V) over the cache
+// KV-cache decode (L == 1, B <= 32) is HBM-bound (weights + cache streamed once per step): "skinny" fp32
+// kernels, one warp per output-column pair, batch rows in registers, x staged in shared memory:
+//   lm_gemv<MODE>  fused RMSNorm -> projection -> {RoPE + cache append | residual | SwiGLU | arg-max partials}
+//   lm_decode_attn one CTA per (batch, head), scores in shared memory
+//   lm_argmax_embed range-restricted greedy token + next input embedding + position bump
+// All decode state (position, token range, output slot) lives in device memory so that one decode step is a
+// fixed launch sequence that can be captured in a CUDA graph and replayed.
+#include <atomic>
+
+#include "common.cuh"
+#include "quark_b200.h"
+
+namespace qb {
+extern std::atomic<long long> g_launches;
+
+// ------------------------------------------------------------------------------------------ prefill
+__global__ void lm_qkv_prep_kernel(const float* __restrict__ qkv, int L, int H, int pos0, const float* __restrict__ rcos,
+                                   const float* __restrict__ rsin, float* __restrict__ q32, float* __restrict__ kc,
+                                   float* __restrict__ vc, int Lmax, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int d = (int)(i & 31);
+  long long r = i >> 5;
+  const int h = (int)(r % H);
+  r /= H;
+  const int t = (int)(r % L);
+  const long long b = r / L;
+  const int pos = pos0 + t;
+  const float* base = qkv + (b * L + t) * 3LL * H * 64 + h * 64;
+  const float c1 = rcos[pos * 64 + d], s1 = rsin[pos * 64 + d], c2 = rcos[pos * 64 + d + 32], s2 = rsin[pos * 64 + d + 32];
+  const long long oq = ((b * H + h) * L + t) * 64 + d;
+  const long long oc = ((b * H + h) * (long long)Lmax + pos) * 64 + d;
+  {
+    const float x1 = base[d], x2 = base[d + 32];
+    q32[oq] = (x1 * c1 - x2 * s1) * 0.125f;
+    q32[oq + 32] = (x2 * c2 + x1 * s2) * 0.125f;
+  }
+  {
+    const float x1 = base[H * 64 + d], x2 = base[H * 64 + d + 32];
+    kc[oc] = x1 * c1 - x2 * s1;
+    kc[oc + 32] = x2 * c2 + x1 * s2;
+  }
+  vc[oc] = base[2 * H * 64 + d];
+  vc[oc + 32] = base[2 * H * 64 + d + 32];
+}
+
+constexpr int LF_BQ = 64, LF_BK = 64, LF_D = 64, LF_P = 72;
+
+__device__ __forceinline__ void l_ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void l_ldsm_x4_t(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void l_mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t l_pack(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// q32 [B,H,L,64] (RoPE'd, pre-scaled); fp32 cache kc/vc [B,H,Lmax,64]; query t sits at absolute position
+// pos0 + t and sees keys <= it.  Operands are split into fp16 hi/lo planes while being staged into shared
+// memory and both products run as 3-term split MMAs (hi*hi + lo*hi + hi*lo): ~2^-21 relative, which the
+// 1e-3 logit tolerance needs once attention scores are O(10) (single-pass fp16 gives ~|s| * 2^-11).
+__device__ __forceinline__ void stage_split8(const float* __restrict__ src, bool ok, __half* dst_hi, __half* dst_lo) {
+  float v[8];
+  if (ok) {
+    const float4 a = *reinterpret_cast<const float4*>(src), c = *reinterpret_cast<const float4*>(src + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  }
+  __half2 h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 bk = __half22float2(h[i]);
+    l[i] = __floats2half2_rn(v[2 * i] - bk.x, v[2 * i + 1] - bk.y);
+  }
+  *reinterpret_cast<uint4*>(dst_hi) = *reinterpret_cast<uint4*>(h);
+  *reinterpret_cast<uint4*>(dst_lo) = *reinterpret_cast<uint4*>(l);
+}
+
+__global__ void __launch_bounds__(128)
+lm_flash_attn_kernel(const float* __restrict__ q32, const float* __restrict__ kc, const float* __restrict__ vc, int L,
+                     int H, int pos0, int Lmax, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  extern __shared__ __align__(16) __half lsm[];
+  __half* sqh = lsm;
+  __half* sql = sqh + LF_BQ * LF_P;
+  __half* skh = sql + LF_BQ * LF_P;
+  __half* skl = skh + LF_BK * LF_P;
+  __half* svh = skl + LF_BK * LF_P;
+  __half* svl = svh + LF_BK * LF_P;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q0 = blockIdx.x * LF_BQ, h = blockIdx.y, b = blockIdx.z;
+  const long long qhead = ((long long)b * H + h) * L * LF_D;
+  const long long chead = ((long long)b * H + h) * (long long)Lmax * LF_D;
+  for (int c = tid; c < LF_BQ * 8; c += 128) {
+    const int r = c >> 3, ch = c & 7;
+    stage_split8(q32 + qhead + (long long)(q0 + r) * LF_D + ch * 8, q0 + r < L, sqh + r * LF_P + ch * 8, sql + r * LF_P + ch * 8);
+  }
+  __syncthreads();
+  uint32_t qh[4][4], ql[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int off = (warp * 16 + (lane & 15)) * LF_P + ks * 16 + (lane >> 4) * 8;
+    l_ldsm_x4(qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3], sqh + off);
+    l_ldsm_x4(ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3], sql + off);
+  }
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[j][e] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const float LOG2E = 1.4426950408889634f;
+  const int qa = q0 + warp * 16 + (lane >> 2), qb = qa + 8;     // this thread's two query rows
+  const int kv_end = min(pos0 + L, pos0 + q0 + LF_BQ);           // causal: no key beyond the tile's last query
+  for (int k0 = 0; k0 < kv_end; k0 += LF_BK) {
+    __syncthreads();
+    for (int c = tid; c < LF_BK * 8; c += 128) {
+      const int r = c >> 3, ch = c & 7;
+      const bool ok = k0 + r < kv_end;
+      const long long g = chead + (long long)(k0 + r) * LF_D + ch * 8;
+      stage_split8(kc + g, ok, skh + r * LF_P + ch * 8, skl + r * LF_P + ch * 8);
+      stage_split8(vc + g, ok, svh + r * LF_P + ch * 8, svl + r * LF_P + ch * 8);
+    }
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[j][e] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int kp = 0; kp < 2; ++kp) {
+        const int off = (j * 8 + (lane & 7)) * LF_P + kp * 32 + (lane >> 3) * 8;
+        uint32_t b0, b1, b2, b3, c0, c1, c2, c3;
+        l_ldsm_x4(b0, b1, b2, b3, skh + off);
+        l_ldsm_x4(c0, c1, c2, c3, skl + off);
+        l_mma(s[j], qh[2 * kp][0], qh[2 * kp][1], qh[2 * kp][2], qh[2 * kp][3], b0, b1);
+        l_mma(s[j], ql[2 * kp][0], ql[2 * kp][1], ql[2 * kp][2], ql[2 * kp][3], b0, b1);
+        l_mma(s[j], qh[2 * kp][0], qh[2 * kp][1], qh[2 * kp][2], qh[2 * kp][3], c0, c1);
+        l_mma(s[j], qh[2 * kp + 1][0], qh[2 * kp + 1][1], qh[2 * kp + 1][2], qh[2 * kp + 1][3], b2, b3);
+        l_mma(s[j], ql[2 * kp + 1][0], ql[2 * kp + 1][1], ql[2 * kp + 1][2], ql[2 * kp + 1][3], b2, b3);
+        l_mma(s[j], qh[2 * kp + 1][0], qh[2 * kp + 1][1], qh[2 * kp + 1][2], qh[2 * kp + 1][3], c2, c3);
+      }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int key = k0 + j * 8 + (lane & 3) * 2;
+      if (key > pos0 + qa) s[j][0] = -INFINITY;
+      if (key + 1 > pos0 + qa) s[j][1] = -INFINITY;
+      if (key > pos0 + qb) s[j][2] = -INFINITY;
+      if (key + 1 > pos0 + qb) s[j][3] = -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    // rows beyond L (tail tile) may see no valid key: keep them finite
+    const float e0 = (mn0 == -INFINITY) ? 0.f : mn0, e1 = (mn1 == -INFINITY) ? 0.f : mn1;
+    const float c0 = exp2f((m0 - e0) * LOG2E), c1 = exp2f((m1 - e1) * LOG2E);
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = exp2f((s[j][0] - e0) * LOG2E);
+      s[j][1] = exp2f((s[j][1] - e0) * LOG2E);
+      s[j][2] = exp2f((s[j][2] - e1) * LOG2E);
+      s[j][3] = exp2f((s[j][3] - e1) * LOG2E);
+      rs0 += s[j][0] + s[j][1];
+      rs1 += s[j][2] + s[j][3];
+    }
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+    m0 = mn0;
+    m1 = mn1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1; }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {   // e: (tile 2ks | 2ks+1) x (cols 0,1 | 2,3) in A-fragment order
+        const int jj = 2 * ks + (e >> 1), cc = (e & 1) * 2;
+        const __half2 hh = __floats2half2_rn(s[jj][cc], s[jj][cc + 1]);
+        const float2 bk = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(s[jj][cc] - bk.x, s[jj][cc + 1] - bk.y);
+        ah[e] = *reinterpret_cast<const uint32_t*>(&hh);
+        al[e] = *reinterpret_cast<const uint32_t*>(&ll);
+      }
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        const int off = (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LF_P + jp * 16 + (lane >> 4) * 8;
+        uint32_t b0, b1, b2, b3, d0, d1, d2, d3;
+        l_ldsm_x4_t(b0, b1, b2, b3, svh + off);
+        l_ldsm_x4_t(d0, d1, d2, d3, svl + off);
+        l_mma(o[2 * jp], ah[0], ah[1], ah[2], ah[3], b0, b1);
+        l_mma(o[2 * jp], al[0], al[1], al[2], al[3], b0, b1);
+        l_mma(o[2 * jp], ah[0], ah[1], ah[2], ah[3], d0, d1);
+        l_mma(o[2 * jp + 1], ah[0], ah[1], ah[2], ah[3], b2, b3);
+        l_mma(o[2 * jp + 1], al[0], al[1], al[2], al[3], b2, b3);
+        l_mma(o[2 * jp + 1], ah[0], ah[1], ah[2], ah[3], d2, d3);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int d = j * 8 + (lane & 3) * 2;
+    if (qa < L) {
+      const long long off = ((long long)b * L + qa) * (long long)(H * LF_D) + h * LF_D + d;
+      __half ha, hb, la, lb;
+      split_f16(o[j][0] * i0, ha, la);
+      split_f16(o[j][1] * i0, hb, lb);
+      *reinterpret_cast<__half2*>(out_hi + off) = __halves2half2(ha, hb);
+      if (out_lo) *reinterpret_cast<__half2*>(out_lo + off) = __halves2half2(la, lb);
+    }
+    if (qb < L) {
+      const long long off = ((long long)b * L + qb) * (long long)(H * LF_D) + h * LF_D + d;
+      __half ha, hb, la, lb;
+      split_f16(o[j][2] * i1, ha, la);
+      split_f16(o[j][3] * i1, hb, lb);
+      *reinterpret_cast<__half2*>(out_hi + off) = __halves2half2(ha, hb);
+      if (out_lo) *reinterpret_cast<__half2*>(out_lo + off) = __halves2half2(la, lb);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ decode step
+enum { LM_QKV = 0, LM_RESID = 1, LM_GATEUP = 2, LM_HEAD = 3 };
+constexpr int LM_KT = 512;      // K chunk staged in shared memory (fp32, 32 rows -> 64 KB)
+constexpr int LM_WARPS = 8;
+
+struct LmGemvParams {
+  const float* x;        // [B,K]
+  int B, K, n_items;
+  const float* W;        // [N,K] fp32
+  const float* W2;       // up-proj rows (GATEUP)
+  const float* norm_w;   // fused pre-RMSNorm weight or NULL
+  float eps;
+  float* out;            // RESID: x [B,N] updated in place; GATEUP: [B,n_items]; QKV: q32 [B,H*64]
+  int N;                 // RESID: output width
+  // QKV
+  int H, Lmax;
+  const int* pos;
+  const float* rcos;
+  const float* rsin;
+  float* kc;
+  float* vc;
+  // HEAD
+  const int* range;      // {lo, hi}
+  float* part_val;       // [gridDim.x, 32]
+  int* part_idx;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(LM_WARPS * 32)
+lm_gemv_kernel(const LmGemvParams p) {
+  extern __shared__ __align__(16) float xs[];   // [32][LM_KT]
+  __shared__ float rstd[32];
+  __shared__ float bval[LM_WARPS][32];
+  __shared__ int bidx[LM_WARPS][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int B = p.B, K = p.K;
+  if (p.norm_w) {
+    for (int b = warp; b < 32; b += LM_WARPS) {
+      float q = 0.f;
+      if (b < B)
+        for (int k = lane; k < K; k += 32) { const float v = p.x[(size_t)b * K + k]; q = fmaf(v, v, q); }
+      q = warp_sum(q);
+      if (lane == 0) rstd[b] = rsqrtf(q / K + p.eps);
+    }
+  }
+  int lo = 0, n_items = p.n_items;
+  if (MODE == LM_HEAD) { lo = p.range[0]; n_items = (p.range[1] - lo) >> 1; }
+  const int item = blockIdx.x * LM_WARPS + warp;
+  const bool active = item < n_items;
+  // column pair of this warp
+  int n0 = 0, n1 = 0, sec = 0, hh = 0, dd = 0;
+  const float* w0p = nullptr;
+  const float* w1p = nullptr;
+  if (active) {
+    if (MODE == LM_QKV) {
+      dd = item & 31; hh = (item >> 5) % p.H; sec = item / (32 * p.H);
+      n0 = sec * p.H * 64 + hh * 64 + dd; n1 = n0 + 32;
+      w0p = p.W + (size_t)n0 * K; w1p = p.W + (size_t)n1 * K;
+    } else if (MODE == LM_GATEUP) {
+      n0 = item; n1 = item;
+      w0p = p.W + (size_t)item * K; w1p = p.W2 + (size_t)item * K;
+    } else {
+      n0 = lo + 2 * item; n1 = n0 + 1;
+      w0p = p.W + (size_t)n0 * K; w1p = p.W + (size_t)n1 * K;
+    }
+  }
+  float acc0[32], acc1[32];
+#pragma unroll
+  for (int b = 0; b < 32; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
+  for (int k0 = 0; k0 < K; k0 += LM_KT) {
+    __syncthreads();
+    for (int e = tid; e < 32 * (LM_KT / 4); e += LM_WARPS * 32) {
+      const int b = e / (LM_KT / 4), c4 = e - b * (LM_KT / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b < B && k0 + c4 * 4 < K) {
+        v = *reinterpret_cast<const float4*>(p.x + (size_t)b * K + k0 + c4 * 4);
+        if (p.norm_w) {
+          const float4 g = *reinterpret_cast<const float4*>(p.norm_w + k0 + c4 * 4);
+          const float r = rstd[b];
+          v.x *= r * g.x; v.y *= r * g.y; v.z *= r * g.z; v.w *= r * g.w;
+        }
+      }
+      *reinterpret_cast<float4*>(xs + (size_t)b * LM_KT + c4 * 4) = v;
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < LM_KT / 128; ++i) {
+        const int kk = i * 128 + lane * 4;
+        if (k0 + kk < K) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(w0p + k0 + kk));
+          const float4 c = __ldg(reinterpret_cast<const float4*>(w1p + k0 + kk));
+#pragma unroll
+          for (int b = 0; b < 32; ++b) {
+            const float4 xv = *reinterpret_cast<const float4*>(xs + (size_t)b * LM_KT + kk);
+            acc0[b] = fmaf(xv.x, a.x, fmaf(xv.y, a.y, fmaf(xv.z, a.z, fmaf(xv.w, a.w, acc0[b]))));
+            acc1[b] = fmaf(xv.x, c.x, fmaf(xv.y, c.y, fmaf(xv.z, c.z, fmaf(xv.w, c.w, acc1[b]))));
+          }
+        }
+      }
+    }
+  }
+  // lane b keeps the totals of batch row b
+  float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+  for (int b = 0; b < 32; ++b) {
+    const float t0 = warp_sum(acc0[b]), t1 = warp_sum(acc1[b]);
+    if (lane == b) { r0 = t0; r1 = t1; }
+  }
+  const int b = lane;
+  if (MODE == LM_HEAD) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    if (active && b < B) {
+      bv = r0; bi = n0;
+      if (r1 > bv) { bv = r1; bi = n1; }     // ties -> lower index (n0 < n1)
+    }
+    bval[warp][lane] = bv;
+    bidx[warp][lane] = bi;
+    __syncthreads();
+    if (warp == 0) {
+      for (int w = 1; w < LM_WARPS; ++w) {
+        const float v = bval[w][lane];
+        const int ix = bidx[w][lane];
+        if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+      }
+      p.part_val[(size_t)blockIdx.x * 32 + lane] = bv;
+      p.part_idx[(size_t)blockIdx.x * 32 + lane] = bi;
+    }
+    return;
+  }
+  if (!active || b >= B) return;
+  if (MODE == LM_RESID) {
+    p.out[(size_t)b * p.N + n0] += r0;
+    p.out[(size_t)b * p.N + n1] += r1;
+  } else if (MODE == LM_GATEUP) {
+    p.out[(size_t)b * p.n_items + item] = silu_f(r0) * r1;
+  } else {  // LM_QKV
+    const int pos = *p.pos;
+    if (sec < 2) {
+      const float c1 = p.rcos[pos * 64 + dd], s1 = p.rsin[pos * 64 + dd];
+      const float c2 = p.rcos[pos * 64 + dd + 32], s2 = p.rsin[pos * 64 + dd + 32];
+      const float y0 = r0 * c1 - r1 * s1, y1 = r1 * c2 + r0 * s2;
+      if (sec == 0) {
+        p.out[(size_t)b * p.H * 64 + hh * 64 + dd] = y0 * 0.125f;
+        p.out[(size_t)b * p.H * 64 + hh * 64 + dd + 32] = y1 * 0.125f;
+      } else {
+        const size_t o = (((size_t)b * p.H + hh) * p.Lmax + pos) * 64 + dd;
+        p.kc[o] = y0;
+        p.kc[o + 32] = y1;
+      }
+    } else {
+      const size_t o = (((size_t)b * p.H + hh) * p.Lmax + pos) * 64 + dd;
+      p.vc[o] = r0;
+      p.vc[o + 32] = r1;
+    }
+  }
+}
+
+// one CTA per (head, batch row): q [B,H*64] fp32 (scaled), fp32 cache, keys 0..pos inclusive
+__global__ void __launch_bounds__(128)
+lm_decode_attn_kernel(const float* __restrict__ q, const float* __restrict__ kc, const float* __restrict__ vc, int H,
+                      int Lmax, const int* __restrict__ posp, float* __restrict__ out) {
+  extern __shared__ float sc[];   // [Lmax] scores
+  __shared__ __align__(16) float qs[64];
+  __shared__ float red[4];
+  __shared__ float part[2][64];
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = *posp + 1;
+  if (tid < 64) qs[tid] = q[(size_t)b * H * 64 + h * 64 + tid];
+  __syncthreads();
+  const float* kb = kc + ((size_t)b * H + h) * Lmax * 64;
+  const float* vb = vc + ((size_t)b * H + h) * Lmax * 64;
+  float mx = -INFINITY;
+  for (int j = tid; j < n; j += 128) {
+    const float4* kr = reinterpret_cast<const float4*>(kb + (size_t)j * 64);
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float4 v = kr[c];
+      const float4 qq = *reinterpret_cast<const float4*>(qs + 4 * c);
+      acc = fmaf(qq.x, v.x, fmaf(qq.y, v.y, fmaf(qq.z, v.z, fmaf(qq.w, v.w, acc))));
+    }
+    sc[j] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = tid; j < n; j += 128) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = red[0] + red[1] + red[2] + red[3];
+  const int d = tid & 63, half = tid >> 6;
+  float acc = 0.f;
+  for (int j = half; j < n; j += 2) acc = fmaf(sc[j], vb[(size_t)j * 64 + d], acc);
+  part[half][d] = acc;
+  __syncthreads();
+  if (tid < 64) out[(size_t)b * H * 64 + h * 64 + tid] = (part[0][tid] + part[1][tid]) / sum;
+}
+
+// greedy token from the head partials, next input embedding, position / slot bump
+__global__ void lm_argmax_embed_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int n_part,
+                                       int B, const float* __restrict__ emb, int Hd, float* __restrict__ x_next,
+                                       int64_t* __restrict__ out_ids, int out_stride, int* __restrict__ pos,
+                                       int* __restrict__ slot) {
+  const int b = blockIdx.x;
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < n_part; i += blockDim.x) {
+    const float v = part_val[(size_t)i * 32 + b];
+    const int ix = part_idx[(size_t)i * 32 + b];
+    if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
+    si[0] = bi;
+    out_ids[(size_t)b * out_stride + *slot] = (int64_t)bi;
+  }
+  __syncthreads();
+  const int tok = si[0];
+  for (int k = threadIdx.x; k < Hd; k += blockDim.x) x_next[(size_t)b * Hd + k] = emb[(size_t)tok * Hd + k];
+  // every block has read *slot before any block can finish? no: use a grid-wide last-block bump instead
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int done = atomicAdd(slot + 1, 1);          // slot[1] = arrival counter
+    if (done == B - 1) { slot[1] = 0; *slot += 1; *pos += 1; }
+  }
+}
+
+}  // namespace qb
+using namespace qb;
+
+extern "C" int qb_lm_qkv_prep(const float* qkv, int64_t B, int64_t L, int32_t heads, int32_t pos0, const float* rope_cos,
+                              const float* rope_sin, float* q32, float* k_cache, float* v_cache, int32_t Lmax,
+                              void* stream) {
+  QB_REQUIRE(qkv && rope_cos && rope_sin && q32 && k_cache && v_cache && pos0 + L <= Lmax, "lm_qkv_prep: bad args");
+  const long long total = B * L * heads * 32;
+  lm_qkv_prep_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      qkv, (int)L, heads, pos0, rope_cos, rope_sin, q32, k_cache, v_cache, Lmax, total);
+  g_launches++;
+  QB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int qb_lm_flash_attn(const float* q32, const float* k_cache, const float* v_cache, int64_t B, int64_t L,
+                                int32_t heads, int32_t pos0, int32_t Lmax, qb_half* out_hi, qb_half* out_lo, void* stream) {
+  QB_REQUIRE(q32 && k_cache && v_cache && out_hi && L > 0, "lm_flash_attn: bad args");
+  dim3 grid((unsigned)ceil_div(L, LF_BQ), (unsigned)heads, (unsigned)B);
+  const size_t smem = (size_t)(2 * LF_BQ + 4 * LF_BK) * LF_P * sizeof(__half);
+  static bool set = false;
+  if (!set) {
+    QB_CHECK_CUDA(cudaFuncSetAttribute(lm_flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set = true;
+  }
+  lm_flash_attn_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(q32, k_cache, v_cache, (int)L, heads, pos0, Lmax,
+                                                                 (__half*)out_hi, (__half*)out_lo);
+  g_launches++;
+  QB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int MODE>
+static int launch_gemv(const LmGemvParams& p, int n_items_max, cudaStream_t st) {
+  static bool set = false;
+  const size_t smem = (size_t)32 * LM_KT * sizeof(float);
+  if (!set) {
+    QB_CHECK_CUDA(cudaFuncSetAttribute(lm_gemv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set = true;
+  }
+  lm_gemv_kernel<MODE><<<(unsigned)ceil_div(n_items_max, LM_WARPS), LM_WARPS * 32, smem, st>>>(p);
+  g_launches++;
+  QB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int qb_lm_decode_layer(float* x, int64_t B, int32_t hidden, int32_t heads, int32_t inter, const float* in_norm,
+                                  const float* wqkv, const float* wo, const float* post_norm, const float* wgate,
+                                  const float* wup, const float* wdown, float* k_cache, float* v_cache, int32_t Lmax,
+                                  const int32_t* pos, const float* rope_cos, const float* rope_sin, float* q_buf,
+                                  float* attn_buf, float* mlp_buf, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  QB_REQUIRE(B >= 1 && B <= 32, "lm_decode_layer: batch must be 1..32 (got %lld)", (long long)B);
+  QB_REQUIRE(hidden == heads * 64 && hidden % 128 == 0 && inter % 128 == 0, "lm_decode_layer: unsupported dims");
+  LmGemvParams p = {};
+  p.B = (int)B; p.eps = 1e-6f; p.H = heads; p.Lmax = Lmax; p.pos = pos; p.rcos = rope_cos; p.rsin = rope_sin;
+  p.kc = k_cache; p.vc = v_cache;
+  // RMSNorm + QKV + RoPE + cache append
+  p.x = x; p.K = hidden; p.W = wqkv; p.norm_w = in_norm; p.out = q_buf; p.n_items = 3 * heads * 32;
+  if (int e = launch_gemv<LM_QKV>(p, p.n_items, st)) return e;
+  static bool attn_set = false;
+  const size_t asmem = (size_t)Lmax * sizeof(float);
+  if (!attn_set) {
+    QB_CHECK_CUDA(cudaFuncSetAttribute(lm_decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attn_set = true;
+  }
+  QB_REQUIRE(asmem <= 64 * 1024, "lm_decode_layer: Lmax too large for the score buffer");
+  lm_decode_attn_kernel<<<dim3((unsigned)heads, (unsigned)B), 128, asmem, st>>>(q_buf, k_cache, v_cache, heads, Lmax, pos,
+                                                                              attn_buf);
+  g_launches++;
+  // o_proj + residual
+  p.x = attn_buf; p.K = hidden; p.W = wo; p.norm_w = nullptr; p.out = x; p.N = hidden; p.n_items = hidden / 2;
+  if (int e = launch_gemv<LM_RESID>(p, p.n_items, st)) return e;
+  // RMSNorm + gate/up + SwiGLU
+  p.x = x; p.K = hidden; p.W = wgate; p.W2 = wup; p.norm_w = post_norm; p.out = mlp_buf; p.n_items = inter;
+  if (int e = launch_gemv<LM_GATEUP>(p, p.n_items, st)) return e;
+  // down + residual
+  p.x = mlp_buf; p.K = inter; p.W = wdown; p.W2 = nullptr; p.norm_w = nullptr; p.out = x; p.N = hidden; p.n_items = hidden / 2;
+  if (int e = launch_gemv<LM_RESID>(p, p.n_items, st)) return e;
+  QB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int qb_lm_head_argmax(const float* x, int64_t B, int32_t hidden, const float* final_norm, const float* w_head,
+                                 const int32_t* range, int32_t max_cols, const float* embedding, float* x_next,
+                                 int64_t* out_ids, int32_t out_stride, int32_t* pos, int32_t* slot, float* part_val,
+                                 int32_t* part_idx, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  QB_REQUIRE(B >= 1 && B <= 32 && max_cols % 2 == 0, "lm_head_argmax: bad args");
+  LmGemvParams p = {};
+  p.B = (int)B; p.eps = 1e-6f; p.x = x; p.K = hidden; p.W = w_head; p.norm_w = final_norm; p.range = range;
+  p.part_val = part_val; p.part_idx = part_idx; p.n_items = max_cols / 2;
+  if (int e = launch_gemv<LM_HEAD>(p, max_cols / 2, st)) return e;
+  const int n_part = (int)ceil_div(max_cols / 2, LM_WARPS);
+  lm_argmax_embed_kernel<<<(unsigned)B, 128, 0, st>>>(part_val, part_idx, n_part, (int)B, embedding, hidden, x_next,
+                                                     out_ids, out_stride, pos, slot);
+  g_launches++;
+  QB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -75,12 +75,14 @@ lstm_kernel(const float* __restrict__ xp, const __half* __restrict__ whh, int B,
   const int n_chunks = Bp / LSTM_NB;
 
   for (int t = 0; t < T; ++t) {
-    if (t > 0) {  // wait until every CTA has published h_{t-1}
-      if (tid == 0) {
-        const unsigned target = (unsigned)t * (unsigned)G;
+    if (t > 0) {  // wait until every CTA has published h_{t-1}: per-CTA flags (no atomic serialisation)
+      if (warp == 0) {
         unsigned spins = 0;
-        while (ld_acquire_u32(counter) < target) {
-          if (++spins > (1u << 28)) asm volatile("trap;");
+        for (;;) {
+          bool ok = true;
+          for (int c = lane; c < G; c += 32) ok = ok && (ld_acquire_u32(counter + c) >= (unsigned)t);
+          if (__all_sync(0xffffffffu, ok)) break;
+          if (++spins > (1u << 26)) asm volatile("trap;");
         }
       }
       __syncthreads();
@@ -194,7 +196,7 @@ lstm_kernel(const float* __restrict__ xp, const __half* __restrict__ whh, int B,
     // ---- publish h_t
     if (tid == 0) {
       __threadfence();
-      atomicAdd(counter, 1u);
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(counter + blockIdx.x), "r"((unsigned)(t + 1)) : "memory");
     }
   }
 }
@@ -212,7 +214,7 @@ using namespace qb;
 
 extern "C" int64_t qb_lstm_workspace_bytes(int64_t B, int64_t H) {
   const int64_t Bp = ceil_div(B, LSTM_NB) * LSTM_NB;
-  return 2 * Bp * H * 2 + 256;
+  return 2 * Bp * H * 2 + 4096;
 }
 
 extern "C" int qb_lstm(const float* xp, const qb_half* whh_hi, const qb_half* whh_lo, int64_t B, int64_t T, int64_t H,

@@ -1,0 +1,329 @@
+"""UniSE AR-LM (`LLM_SFT`) with the reference's surface, running on libquark_b200.
+
+Mirrors QuarkAudio-UniSE/model/llm/llm_sft.py:13-195 and llm.py:13-228:
+    LLM_SFT(num_tasks, task_map, feats_dim, llm_base_config)
+    .llm_forward(inputs_embeds, past_key_values=None, use_cache=False) -> .last_hidden_state / .past_key_values
+    .forward(task_name, enroll_mel, enroll_feats, mix_mel, mix_feats, global_ids, semantic_ids) -> (loss, acc)
+    .generate(task_name, enroll_mel, enroll_feats, mix_mel, mix_feats, global_length=32, ..., do_sample) -> (global, semantic)
+state_dict keys are the reference's (HF Llama layer names under `layers.*`, `norm.weight`, `codec_embedding`,
+`output_head`, `adapter`, `task_embedding`, `enroll_sos_embedding`, `mix_sos_embedding`); the conformer
+condition encoder (`cond_*`, built but never executed: llm_sft.py:62-65,112-115) is accepted at load and ignored.
+
+Prefill / teacher-forced forward: tcgen05 GEMMs (3-term split) + causal split-precision flash attention over a static fp32 KV cache.
+Decode: fused skinny fp32 kernels, one CUDA graph per step replayed 33 + T times; greedy (do_sample=False, the shipped
+setting U/model/model.py:173).  No PyTorch / CPU fallback for the transformer stack.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from .codec import _Tree
+from .ops import ACT_SWIGLU, Planes, rowmap
+
+
+def lm_spec(cfg_base: dict, num_tasks: int, feats_dim: int):
+    H, L = cfg_base["hidden_size"], cfg_base["num_layers"]
+    V = 3 + cfg_base["global_size"] + cfg_base["semantic_size"]
+    out = {"mix_sos_embedding.weight": (1, H), "codec_embedding.weight": (V, H)}
+    for i in range(L):
+        p = f"layers.{i}."
+        for n in "qkvo":
+            out[p + f"self_attn.{n}_proj.weight"] = (H, H)
+        out[p + "mlp.gate_proj.weight"] = (4 * H, H)
+        out[p + "mlp.up_proj.weight"] = (4 * H, H)
+        out[p + "mlp.down_proj.weight"] = (H, 4 * H)
+        out[p + "input_layernorm.weight"] = (H,)
+        out[p + "post_attention_layernorm.weight"] = (H,)
+    out["norm.weight"] = (H,)
+    out["output_head.weight"] = (V, H)
+    out["task_embedding.weight"] = (num_tasks, H)
+    out["enroll_sos_embedding.weight"] = (1, H)
+    out["adapter.weight"] = (H, feats_dim)
+    out["adapter.bias"] = (H,)
+    return out
+
+
+class StaticKVCache:
+    """Pre-allocated fp32 cache [layers][B, heads, Lmax, 64]; replaces HF DynamicCache's torch.cat growth."""
+
+    def __init__(self, layers, B, heads, Lmax, device):
+        self.k = [torch.zeros(B, heads, Lmax, 64, dtype=torch.float32, device=device) for _ in range(layers)]
+        self.v = [torch.zeros(B, heads, Lmax, 64, dtype=torch.float32, device=device) for _ in range(layers)]
+        self.B, self.Lmax, self.length = B, Lmax, 0
+        self.pos = torch.zeros(1, dtype=torch.int32, device=device)     # device copy used by the decode kernels
+
+    def get_seq_length(self):
+        return self.length
+
+
+@dataclass
+class LMOutput:
+    last_hidden_state: torch.Tensor
+    past_key_values: Optional[StaticKVCache] = None
+
+
+class LLM_SFT(nn.Module):
+    def __init__(self, num_tasks: int = 1, task_map: dict = None, feats_dim: int = 768, llm_base_config: dict = None):
+        super().__init__()
+        b = dict(llm_base_config or {})
+        self.cfg = b
+        self.task_map = dict(task_map or {"se": 0})
+        self.hidden, self.n_layers, self.heads = b["hidden_size"], b["num_layers"], b["num_attention_heads"]
+        if self.hidden != self.heads * 64 or self.hidden % 128:
+            raise ValueError("kernels assume head_dim 64 and hidden % 128 == 0 (shipped config: 512 = 8 x 64)")
+        self.global_size, self.semantic_size = b["global_size"], b["semantic_size"]
+        self.vocab_size = 3 + self.global_size + self.semantic_size
+        self.global_offset, self.semantic_offset = 3, 3 + self.global_size
+        self.global_sos_token_id, self.semantic_sos_token_id, self.semantic_eos_token_id = 0, 1, 2
+        self.label_smoothing = b.get("label_smoothing", 0.1)
+        self.max_pos = b.get("max_position_embeddings", 4096)
+        tree = _Tree.build(lm_spec(b, num_tasks, feats_dim))
+        for name, child in tree.named_children():
+            self.add_module(name, child)
+        self._w, self._ws = None, {}
+        self.eval()
+
+    # ------------------------------------------------------------------ state
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        sd = {k: v for k, v in state_dict.items() if not k.startswith(("cond_", "rotary_emb."))}
+        r = super().load_state_dict(sd, strict=strict, assign=assign)
+        self._w = None
+        return r
+
+    def _apply(self, fn, *a, **k):
+        self._w, self._ws = None, {}
+        return super()._apply(fn, *a, **k)
+
+    def _dev(self):
+        return self.norm.weight.device
+
+    def _prepare(self):
+        if self._w is not None:
+            return self._w
+        dev = self._dev()
+        if dev.type != "cuda":
+            raise RuntimeError("unified_audio_b200.LLM_SFT runs on CUDA only (no CPU fallback): call .cuda() first")
+        sd = {k: v.detach().float() for k, v in self.state_dict().items()}
+        layers = []
+        for i in range(self.n_layers):
+            p = f"layers.{i}."
+            wqkv = torch.cat([sd[p + f"self_attn.{n}_proj.weight"] for n in "qkv"], 0).contiguous()
+            wg, wu = sd[p + "mlp.gate_proj.weight"].contiguous(), sd[p + "mlp.up_proj.weight"].contiguous()
+            layers.append(dict(
+                in_w=sd[p + "input_layernorm.weight"].contiguous(), post_w=sd[p + "post_attention_layernorm.weight"].contiguous(),
+                wqkv=Planes.from_f32(wqkv, True), wo=Planes.from_f32(sd[p + "self_attn.o_proj.weight"], True),
+                wgu=Planes.from_f32(torch.stack([wg, wu], 1).reshape(-1, self.hidden), True),
+                wd=Planes.from_f32(sd[p + "mlp.down_proj.weight"], True),
+                wqkv32=wqkv, wo32=sd[p + "self_attn.o_proj.weight"].contiguous(), wg32=wg, wu32=wu,
+                wd32=sd[p + "mlp.down_proj.weight"].contiguous()))
+        inv = 1.0 / (10000.0 ** (torch.arange(0, 64, 2, dtype=torch.int64).float() / 64))
+        fr = torch.arange(self.max_pos).float()[:, None] * inv[None, :]
+        emb = torch.cat((fr, fr), -1)
+        self._w = dict(layers=layers, norm=sd["norm.weight"].contiguous(), head=Planes.from_f32(sd["output_head.weight"], True),
+                       head32=sd["output_head.weight"].contiguous(), emb=sd["codec_embedding.weight"].contiguous(),
+                       adapter=Planes.from_f32(sd["adapter.weight"], True), adapter_b=sd["adapter.bias"].contiguous(),
+                       cos=emb.cos().to(dev).contiguous(), sin=emb.sin().to(dev).contiguous())
+        return self._w
+
+    def _buf(self, name, shape, dtype=torch.float32):
+        key = (name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None:
+            t = torch.zeros(shape, dtype=dtype, device=self._dev())
+            self._ws[key] = t
+        return t
+
+    def _planes(self, name, shape):
+        key = ("P", name, tuple(shape))
+        p = self._ws.get(key)
+        if p is None:
+            p = Planes.zeros(shape, True, self._dev())
+            self._ws[key] = p
+        return p
+
+    # ------------------------------------------------------------------ transformer stack
+    def _prefill(self, x: torch.Tensor, B: int, L: int, cache: StaticKVCache):
+        """x [B*L, hidden] fp32, updated in place by the 12 layers; K/V written at cache.length.."""
+        W = self._prepare()
+        H, heads, inter, M = self.hidden, self.heads, 4 * self.hidden, B * L
+        pos0 = cache.length
+        if pos0 + L > cache.Lmax:
+            raise ValueError("KV cache too small")
+        t1 = self._planes("t1", (M, H))
+        hid = self._planes("hid", (M, inter))
+        qkv = self._buf("qkv", (M, 3 * H))
+        q16 = self._buf("q32", (B, heads, L, 64))
+        xm = rowmap(x, H, M, 0)
+        lin = lambda a, w, n, K, **kw: ops.gemm(a, w, n, a_batch=1, a_rows_per_batch=M, a_ld=K, m_per_batch=M, **kw)
+        for i, Lw in enumerate(W["layers"]):
+            ops.rmsnorm(x, Lw["in_w"], M, H, t1)
+            lin(t1, Lw["wqkv"], 3 * H, H, out_f32=rowmap(qkv, 3 * H, M, 0))
+            ops.lm_qkv_prep(qkv, B, L, heads, pos0, W["cos"], W["sin"], q16, cache.k[i], cache.v[i], cache.Lmax)
+            ops.lm_flash_attn(q16, cache.k[i], cache.v[i], B, L, heads, pos0, cache.Lmax, t1)
+            lin(t1, Lw["wo"], H, H, residual=xm, out_f32=xm)
+            ops.rmsnorm(x, Lw["post_w"], M, H, t1)
+            lin(t1, Lw["wgu"], 2 * inter, H, act=ACT_SWIGLU, out_planes=hid, out_planes_map=(inter, M, 0))
+            lin(hid, Lw["wd"], H, inter, residual=xm, out_f32=xm)
+        cache.length = pos0 + L
+        cache.pos.fill_(cache.length)
+
+    def _decode_layers(self, x: torch.Tensor, B: int, cache: StaticKVCache):
+        W = self._prepare()
+        H, heads, inter = self.hidden, self.heads, 4 * self.hidden
+        qb, ab, mb = self._buf("dq", (B, H)), self._buf("da", (B, H)), self._buf("dm", (B, inter))
+        for i, Lw in enumerate(W["layers"]):
+            ops.lm_decode_layer(x, B, H, heads, inter, Lw, cache.k[i], cache.v[i], cache.Lmax, cache.pos, W["cos"], W["sin"],
+                                qb, ab, mb)
+
+    @torch.no_grad()
+    def llm_forward(self, inputs_embeds, attention_mask=None, past_key_values: Optional[StaticKVCache] = None,
+                    use_cache: bool = False, **unused) -> LMOutput:
+        """llm.py:150-228 (mask None + SDPA == causal)."""
+        if attention_mask is not None:
+            raise NotImplementedError("only the reference's causal (mask=None) path is implemented")
+        W = self._prepare()
+        B, L, H = inputs_embeds.shape
+        cache = past_key_values
+        if cache is None:
+            cache = StaticKVCache(self.n_layers, B, self.heads, max(64, -(-L // 64) * 64 + (1024 if use_cache else 0)), self._dev())
+        x = inputs_embeds.float().reshape(B * L, H).contiguous().clone()
+        if L == 1 and B <= 32 and cache.length > 0:
+            self._decode_layers(x, B, cache)
+            cache.length += 1
+            cache.pos.fill_(cache.length)
+        else:
+            self._prefill(x, B, L, cache)
+        out = torch.empty(B * L, H, device=x.device)
+        ops.rmsnorm(x, W["norm"], B * L, H, out_f32=out)
+        return LMOutput(out.reshape(B, L, H), cache if use_cache else None)
+
+    # ------------------------------------------------------------------ conditioning prefix (llm_sft.py:58-78)
+    def _adapter(self, feats):
+        W = self._prepare()
+        B, T, Fd = feats.shape
+        fpad = (Fd + 63) // 64 * 64
+        a = Planes.zeros((B * T, fpad), True, feats.device)
+        ops.rows_to_planes(feats.float().contiguous(), 1, B * T, Fd, a, fpad, B * T, 0)
+        wpad = W.get("adapter_pad")
+        if wpad is None:
+            w = torch.zeros(self.hidden, fpad, device=feats.device)
+            w[:, :Fd] = self.adapter.weight.detach().float()
+            wpad = W["adapter_pad"] = Planes.from_f32(w, True)
+        out = torch.empty(B * T, self.hidden, device=feats.device)
+        ops.gemm(a, wpad, self.hidden, a_batch=1, a_rows_per_batch=B * T, a_ld=fpad, m_per_batch=B * T, bias=W["adapter_b"],
+                 out_f32=rowmap(out, self.hidden, B * T, 0))
+        return out.reshape(B, T, self.hidden)
+
+    def _prefix(self, task_name, enroll_feats, mix_feats):
+        B = mix_feats.shape[0]
+        e = lambda w: w.detach().float()
+        task = e(self.task_embedding.weight)[self.task_map[task_name]][None, None].expand(B, 1, -1)
+        mix_sos = e(self.mix_sos_embedding.weight)[0][None, None].expand(B, 1, -1)
+        parts = [task]
+        if enroll_feats is not None:
+            parts += [e(self.enroll_sos_embedding.weight)[0][None, None].expand(B, 1, -1), self._adapter(enroll_feats)]
+        parts += [mix_sos, self._adapter(mix_feats)]
+        return torch.cat(parts, 1)
+
+    # ------------------------------------------------------------------ teacher-forced forward (llm_sft.py:37-89)
+    @torch.no_grad()
+    def forward(self, task_name, enroll_mel, enroll_feats, mix_mel, mix_feats, global_ids, semantic_ids, return_logits=False):
+        W = self._prepare()
+        g = global_ids.long() + self.global_offset
+        s = semantic_ids.long() + self.semantic_offset
+        B = g.shape[0]
+        col = lambda v: torch.full((B, 1), v, dtype=torch.long, device=g.device)
+        input_ids = torch.cat([col(0), g, col(1), s], 1)
+        target_ids = torch.cat([g, col(1), s, col(2)], 1)
+        emb = torch.cat([self._prefix(task_name, enroll_feats if enroll_mel is not None else None, mix_feats),
+                         W["emb"][input_ids]], 1)
+        hs = self.llm_forward(emb).last_hidden_state[:, -target_ids.shape[1]:].contiguous()
+        Lt, V = hs.shape[1], self.vocab_size
+        M = B * Lt
+        hp = Planes.zeros((M, self.hidden), True, hs.device)
+        ops.split_f16(hs.reshape(M, self.hidden), hp)
+        vpad = (V + 3) // 4 * 4
+        logits = torch.empty(M, vpad, device=hs.device)
+        ops.gemm(hp, W["head"], V, a_batch=1, a_rows_per_batch=M, a_ld=self.hidden, m_per_batch=M,
+                 out_f32=rowmap(logits, vpad, M, 0))
+        logits = logits[:, :V].reshape(B, Lt, V)
+        # label-smoothed KL + accuracy (llm.py:87-104): metric glue on the produced logits
+        flat, tgt = logits.reshape(-1, V), target_ids.reshape(-1)
+        true = torch.full_like(flat, self.label_smoothing / (V - 1))
+        true.scatter_(1, tgt[:, None], 1.0 - self.label_smoothing)
+        loss = torch.nn.functional.kl_div(torch.log_softmax(flat, -1), true, reduction="batchmean")
+        acc = (logits.argmax(-1) == target_ids).float().mean()
+        return (loss, acc, logits) if return_logits else (loss, acc)
+
+    # ------------------------------------------------------------------ generate (llm_sft.py:93-195)
+    @torch.no_grad()
+    def generate(self, task_name, enroll_mel, enroll_feats, mix_mel, mix_feats, global_length: int = 32,
+                 temperature: float = 0.8, top_k: int = 50, top_p: float = 0.95, do_sample: bool = True,
+                 use_cuda_graph: bool = True):
+        if do_sample:
+            raise NotImplementedError("only greedy decoding (do_sample=False, the shipped test setting model.py:173) "
+                                      "is implemented natively; top-k/top-p never remove the arg-max (llm.py:263-287)")
+        semantic_length = mix_mel.size(1)
+        Ball = mix_feats.shape[0]
+        outs_g, outs_s = [], []
+        for b0 in range(0, Ball, 32):      # decode kernels keep <= 32 sequences' rows in registers
+            sl = slice(b0, min(b0 + 32, Ball))
+            gi, si = self._generate_chunk(task_name, None if enroll_mel is None else enroll_feats[sl], mix_feats[sl],
+                                          semantic_length, global_length, use_cuda_graph)
+            outs_g.append(gi)
+            outs_s.append(si)
+        return torch.cat(outs_g, 0), torch.cat(outs_s, 0)
+
+    def _generate_chunk(self, task_name, enroll_feats, mix_feats, semantic_length, global_length, use_graph):
+        W = self._prepare()
+        dev = mix_feats.device
+        prefix = self._prefix(task_name, enroll_feats, mix_feats)
+        B, P, H = prefix.shape
+        n_steps = global_length + 1 + semantic_length
+        Lmax = -(-(P + n_steps) // 64) * 64
+        cache = StaticKVCache(self.n_layers, B, self.heads, Lmax, dev)
+        x = prefix.reshape(B * P, H).contiguous().clone()
+        self._prefill(x, B, P, cache)
+        max_cols = max(self.global_size, self.semantic_size)
+        xs = self._buf("gx", (B, H))
+        rng = torch.tensor([self.global_offset, self.global_offset + self.global_size], dtype=torch.int32, device=dev)
+        slot = torch.zeros(2, dtype=torch.int32, device=dev)
+        out_ids = torch.zeros(B, n_steps, dtype=torch.int64, device=dev)
+        pv = self._buf("pv", (max_cols // 16 + 1, 32))
+        pi = self._buf("pi", (max_cols // 16 + 1, 32), torch.int32)
+
+        def step():
+            self._decode_layers(xs, B, cache)
+            ops.lm_head_argmax(xs, B, H, W["norm"], W["head32"], rng, max_cols, W["emb"], xs, out_ids, n_steps, cache.pos,
+                               slot, pv, pi)
+
+        graph = None
+        if use_graph:
+            # warm-up outside capture (one-time cudaFuncSetAttribute calls), then restore the mutated state
+            xs.copy_(W["emb"][self.global_sos_token_id][None].expand(B, H))
+            step()
+            cache.pos.fill_(cache.length)
+            slot.zero_()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            cache.pos.fill_(cache.length)
+            slot.zero_()
+        run = graph.replay if graph is not None else step
+        xs.copy_(W["emb"][self.global_sos_token_id][None].expand(B, H))
+        for _ in range(global_length + 1):
+            run()
+        rng.copy_(torch.tensor([self.semantic_offset, self.semantic_offset + self.semantic_size], dtype=torch.int32, device=dev))
+        xs.copy_(W["emb"][self.semantic_sos_token_id][None].expand(B, H))
+        for _ in range(semantic_length):
+            run()
+        cache.length += n_steps
+        global_ids = out_ids[:, :global_length] - self.global_offset
+        semantic_ids = out_ids[:, global_length + 1:] - self.semantic_offset
+        return global_ids, semantic_ids

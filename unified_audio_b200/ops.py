@@ -101,8 +101,10 @@ def layernorm(x, w, b, B, rows, Cc, eps=1e-6, out_f32=None, out: Optional[Planes
                                         rows_per_batch, row_off, _stream()))
 
 
-def rmsnorm(x, w, rows, Cc, out: Planes, eps=1e-6):
-    _lib.check(_lib.load().qb_rmsnorm(_p(x), _p(w), eps, rows, Cc, _p(out.hi), _p(out.lo), _stream()))
+def rmsnorm(x, w, rows, Cc, out: Optional[Planes] = None, eps=1e-6, out_f32=None):
+    hi = out.hi if out is not None else None
+    lo = out.lo if out is not None else None
+    _lib.check(_lib.load().qb_rmsnorm(_p(x), _p(w), eps, rows, Cc, _p(out_f32), _p(hi), _p(lo), _stream()))
 
 
 def dwconv7_ln(x, dw_w, dw_b, ln_w, ln_b, B, T, Cc, out: Planes):
@@ -173,6 +175,29 @@ def rvq_encode(x, codebooks, cb: Planes, neg_half_e2, e2max, M, D, K, nq, idx, q
 
 def rvq_decode(idx, codebooks, M, D, K, nq, out, out_ld, col_off):
     _lib.check(_lib.load().qb_rvq_decode(_p(idx), _p(codebooks), M, D, K, nq, _p(out), out_ld, col_off, _stream()))
+
+
+def lm_qkv_prep(qkv, B, L, heads, pos0, cos, sin, q16, kc, vc, Lmax):
+    _lib.check(_lib.load().qb_lm_qkv_prep(_p(qkv), B, L, heads, pos0, _p(cos), _p(sin), _p(q16), _p(kc), _p(vc), Lmax,
+                                          _stream()))
+
+
+def lm_flash_attn(q16, kc, vc, B, L, heads, pos0, Lmax, out: Planes):
+    _lib.check(_lib.load().qb_lm_flash_attn(_p(q16), _p(kc), _p(vc), B, L, heads, pos0, Lmax, _p(out.hi), _p(out.lo),
+                                            _stream()))
+
+
+def lm_decode_layer(x, B, hidden, heads, inter, L, kc, vc, Lmax, pos, cos, sin, q_buf, attn_buf, mlp_buf):
+    _lib.check(_lib.load().qb_lm_decode_layer(_p(x), B, hidden, heads, inter, _p(L["in_w"]), _p(L["wqkv32"]), _p(L["wo32"]),
+                                              _p(L["post_w"]), _p(L["wg32"]), _p(L["wu32"]), _p(L["wd32"]), _p(kc), _p(vc),
+                                              Lmax, _p(pos), _p(cos), _p(sin), _p(q_buf), _p(attn_buf), _p(mlp_buf),
+                                              _stream()))
+
+
+def lm_head_argmax(x, B, hidden, final_norm, w_head, rng, max_cols, emb, x_next, out_ids, out_stride, pos, slot, pv, pi):
+    _lib.check(_lib.load().qb_lm_head_argmax(_p(x), B, hidden, _p(final_norm), _p(w_head), _p(rng), max_cols, _p(emb),
+                                             _p(x_next), _p(out_ids), out_stride, _p(pos), _p(slot), _p(pv), _p(pi),
+                                             _stream()))
 
 
 def launch_count() -> int:
