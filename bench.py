@@ -197,6 +197,85 @@ def run_reference(args, cfg):
     print(json.dumps(line))
 
 
+def run_lm(args):
+    """Secondary line: UniSE SR AR-LM greedy generate (prefix 252 + 33 + 250 cached steps), B=32 per GPU.
+    tokens/s counts generated tokens (283 per sequence)."""
+    LM = dict(num_tasks=3, task_map=dict(se=0, tse=1, rtse=2), feats_dim=768,
+              llm_base_config=dict(cond_dim=80, global_size=4096, semantic_size=8192, hidden_size=512, num_layers=12,
+                                   num_attention_heads=8, dropout_p=0.1, max_position_embeddings=4096, label_smoothing=0.1))
+    B, T = 32, 250
+    if args.impl == "reference":
+        from oracle import llama
+        sd = llama.make_lm_state_dict(LM, 7, 2.0)
+        Bc = 4
+        mix = torch.randn(Bc, T, 768)
+        torch.set_num_threads(min(32, os.cpu_count() or 1))
+        t0 = time.perf_counter()
+        llama.sft_generate(sd, LM, "se", None, mix, T)
+        dt = time.perf_counter() - t0
+        v = Bc * 283 / dt
+        print(json.dumps(dict(metric="unise_sr_arlm_generate_tokens_per_s", value=v, unit="tokens/s", n_gpus=args.gpus,
+                              steps=1, warmup=0, ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                              dtype="f32", data="synthetic", impl="reference",
+                              config=dict(workload="UniSE SR AR-LM greedy generate, prefix 252 + 283 cached steps", batch=Bc),
+                              cpu_baseline=dict(value=v, unit="tokens/s", cores=torch.get_num_threads(), kind="port",
+                                                sample=f"{Bc} sequences x 283 tokens, oracle port pinned against transformers.LlamaModel"),
+                              e2e=dict(value=v, unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)))
+        return
+    from unified_audio_b200 import ops
+    from unified_audio_b200.llm import LLM_SFT
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    m = LLM_SFT(num_tasks=3, task_map=LM["task_map"], feats_dim=768, llm_base_config=LM["llm_base_config"]).to(dev)
+    g = torch.Generator(device=dev).manual_seed(7)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.dim() >= 2 and "embedding" not in n:
+                p.copy_(torch.randn(p.shape, generator=g, device=dev) * (2.0 / p.shape[-1] ** 0.5))
+            elif p.dim() >= 2:
+                p.copy_(torch.randn(p.shape, generator=g, device=dev))
+            else:
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g, device=dev))
+    m._w = None
+    mix_h = torch.randn(B, T, 768).pin_memory()
+    mix = mix_h.to(dev)
+    for _ in range(max(args.warmup, 1)):
+        m.generate("se", None, None, mix, mix, do_sample=False)
+    ops.launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(args.steps):
+        m.generate("se", None, None, mix, mix, do_sample=False)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = ops.launch_count() // args.steps
+    e0.record()
+    for _ in range(args.steps):
+        gi, si = m.generate("se", None, None, mix_h.to(dev, non_blocking=True), mix_h.to(dev, non_blocking=True), do_sample=False)
+        gi.cpu(); si.cpu()
+    e1.record(); torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    peaks = load_peaks()
+    # bytes per decode step: fp32 layer weights + head slice + fp32 KV read (SURVEY 8d), summed over the 283 steps
+    w_bytes = 12 * (4 * 512 * 512 + 3 * 512 * 2048) * 4
+    kv = sum(B * 2 * 12 * 512 * 4 * (252 + i + 1) for i in range(283))
+    head = 33 * 4096 * 512 * 4 + 250 * 8192 * 512 * 4
+    total_bytes = 283 * w_bytes + head + kv
+    gbs = total_bytes / (ms * 1e-3) / 1e9
+    print(json.dumps(dict(metric="unise_sr_arlm_generate_tokens_per_s", value=B * 283 / (ms * 1e-3), unit="tokens/s", n_gpus=1,
+                          steps=args.steps, warmup=max(args.warmup, 1), ms_per_step=ms, higher_is_better=True, scaling="weak",
+                          vs_baseline=None, dtype="f32 decode / f16x3 prefill", data="synthetic",
+                          config=dict(workload="UniSE SR AR-LM greedy generate (prefill 252 + 33 + 250 cached steps), batch=32",
+                                      batch=B, semantic_length=T),
+                          e2e=dict(value=B * 283 / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=int(mix_h.numel() * 4),
+                                   d2h_bytes_per_step=B * 282 * 8),
+                          gpu_launches=int(launches),
+                          roofline=dict(bound="hbm", achieved=gbs, peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"],
+                                        traffic=None, kernel="decode step (lm_gemv + lm_decode_attn), algorithmic bytes = fp32 "
+                                        "weights + head slice + fp32 KV read per step, whole generate incl. prefill"))))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -208,10 +287,14 @@ def main():
     ap.add_argument("--precision", default="mixed")
     ap.add_argument("--ref-clips", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="codec", choices=["codec", "lm"],
+                    help="codec = BASELINE configs[1] (default, the driver's line); lm = UniSE SR AR-LM generate (configs[2])")
     ap.add_argument("--quick", action="store_true", help="profiling aid: W warm-up + K steps only, no e2e/roofline/cpu legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     cfg = H2_FULL
+    if args.workload == "lm":
+        return run_lm(args)
     if args.impl == "reference":
         return run_reference(args, cfg)
 

@@ -292,6 +292,137 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------ CTA-pair kernel (cta_group::2)
+// A cluster of two CTAs (one TPC) owns a 256 x BN output tile: CTA r holds A rows [r*128, r*128+128) and
+// HALF of the weight tile (rows [r*BN/2, (r+1)*BN/2)); the leader issues tcgen05.mma.cta_group::2 (M = 256)
+// which reads both halves of B across the pair, so each SM ingests A 16 KB + W 16 KB per K-block instead of
+// 16 + 32: the L2 -> SM traffic of the single-pass GEMM drops by a third (it was load-paced, profiles/).
+// Barrier protocol: TMA of both CTAs signals the LEADER's full barrier; the leader's commit is multicast to
+// both CTAs' empty / tmem-full barriers; both epilogues arrive on the leader's tmem-empty barrier.
+template <int BN, int NTERMS, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                const GemmParams p) {
+  constexpr int BM = 128, BK = 64;
+  constexpr int NPL = (NTERMS == 1) ? 1 : 2;
+  constexpr uint32_t A_BYTES = BM * BK * 2, W_BYTES = (BN / 2) * BK * 2;
+  constexpr uint32_t STAGE_BYTES = NPL * (A_BYTES + W_BYTES);
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two <= 512");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * GEMM_EPI_WARPS); }
+    fence_mbar_init();
+  }
+  if (warp == GEMM_EPI_WARPS + 1) { tmem_alloc2(tmem_slot, TMEM_COLS); tmem_relinquish2(); }
+  if (warp == GEMM_EPI_WARPS && lane == 0) {
+    prefetch_tmap(&tmA_hi); prefetch_tmap(&tmW_hi);
+    if (NPL == 2) { prefetch_tmap(&tmA_lo); prefetch_tmap(&tmW_lo); }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+
+  if (warp == GEMM_EPI_WARPS) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+        const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+        const int b = m_tile / p.tiles_per_batch, m0 = (m_tile % p.tiles_per_batch) * 2 * BM + rank * BM;
+        const int n0 = n_tile * BN + rank * (BN / 2);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+          const uint32_t fb = mapa_u32(smem_u32(&full[stage]), 0);
+          uint8_t* s = smem + stage * STAGE_BYTES;
+          const int ax = (tap % p.stride) * p.C + cb * BK, ay = m0 + tap / p.stride, wx = tap * p.C + cb * BK;
+          tma2_load_3d(s, &tmA_hi, fb, ax, ay, b);
+          if (NPL == 2) tma2_load_3d(s + A_BYTES, &tmA_lo, fb, ax, ay, b);
+          tma2_load_2d(s + NPL * A_BYTES, &tmW_hi, fb, wx, n0);
+          if (NPL == 2) tma2_load_2d(s + NPL * A_BYTES + W_BYTES, &tmW_lo, fb, wx, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == GEMM_EPI_WARPS + 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_f16(2 * BM, BN);
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t a_hi = make_sw128_kmajor_desc(sa + k * 32);
+            const uint64_t w_hi = make_sw128_kmajor_desc(sa + NPL * A_BYTES + k * 32);
+            umma2_f16(d_tmem, a_hi, w_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (NTERMS == 3) {
+              const uint64_t a_lo = make_sw128_kmajor_desc(sa + A_BYTES + k * 32);
+              const uint64_t w_lo = make_sw128_kmajor_desc(sa + NPL * A_BYTES + W_BYTES + k * 32);
+              umma2_f16(d_tmem, a_lo, w_hi, idesc, 1u);
+              umma2_f16(d_tmem, a_hi, w_lo, idesc, 1u);
+            }
+          }
+          umma2_commit_mc(&empty[stage], 3);
+          if (kb == p.num_kb - 1) umma2_commit_mc(&tfull[acc], 3);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    constexpr int CPW = BN / (GEMM_EPI_WARPS / 4);
+    const int q = warp & 3, hc = warp >> 2;
+    uint32_t it = 0;
+    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
+      const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+      const int b = m_tile / p.tiles_per_batch, m0 = (m_tile % p.tiles_per_batch) * 2 * BM + rank * BM, n0 = n_tile * BN;
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + hc * CPW;
+#pragma unroll 1
+      for (int c = 0; c < CPW; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c, r);
+        tmem_ld_wait();
+        epilogue_row32(p, b, m0 + q * 32 + lane, n0 + hc * CPW + c, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == GEMM_EPI_WARPS + 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------ SIMT cross-check
 __global__ void gemm_simt_kernel(const GemmParams p) {
   const int N_out = p.act == QB_ACT_SWIGLU ? p.N / 2 : p.N;
@@ -427,6 +558,43 @@ static int launch_tc(const qb_gemm_desc* d, cudaStream_t st, int num_sms) {
   return 0;
 }
 
+template <int BN, int NTERMS, int STAGES>
+static int launch_tc2(const qb_gemm_desc* d, cudaStream_t st, int num_sms) {
+  GemmParams p;
+  if (int e = fill_params(d, &p, BN)) return e;
+  p.tiles_per_batch = (int)ceil_div(d->m_per_batch, 256);      // pair tiles of 256 rows
+  p.num_tiles = (int)(d->a_batch * p.tiles_per_batch * p.num_n_tiles);
+  CUtensorMap mA_hi, mA_lo, mW_hi, mW_lo;
+  const cuuint64_t C = (cuuint64_t)d->a_ld, s = (cuuint64_t)d->stride;
+  cuuint64_t adims[3] = {s * C, (cuuint64_t)d->a_rows_per_batch / s, (cuuint64_t)d->a_batch};
+  cuuint64_t astr[2] = {s * C * 2, (cuuint64_t)d->a_rows_per_batch * C * 2};
+  cuuint32_t abox[3] = {64, 128, 1};
+  cuuint64_t wdims[2] = {(cuuint64_t)d->taps * C, (cuuint64_t)d->n};
+  cuuint64_t wstr[1] = {(cuuint64_t)d->taps * C * 2};
+  cuuint32_t wbox[2] = {64, (cuuint32_t)(BN / 2)};
+  if (int e = make_map(&mA_hi, d->a_hi, 3, adims, astr, abox)) return e;
+  if (int e = make_map(&mW_hi, d->w_hi, 2, wdims, wstr, wbox)) return e;
+  if (NTERMS == 3) {
+    if (int e = make_map(&mA_lo, d->a_lo, 3, adims, astr, abox)) return e;
+    if (int e = make_map(&mW_lo, d->w_lo, 2, wdims, wstr, wbox)) return e;
+  } else {
+    mA_lo = mA_hi; mW_lo = mW_hi;
+  }
+  constexpr int NPL = NTERMS == 1 ? 1 : 2;
+  constexpr size_t smem = (size_t)STAGES * NPL * (128 * 64 * 2 + (BN / 2) * 64 * 2) + 1024 + 256;
+  auto kern = gemm_tc2_kernel<BN, NTERMS, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int clusters = p.num_tiles < num_sms / 2 ? p.num_tiles : num_sms / 2;
+  kern<<<2 * clusters, GEMM_THREADS, smem, st>>>(mA_hi, mA_lo, mW_hi, mW_lo, p);
+  g_launches++;
+  QB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static int num_sms_cached() {
   static int n = 0;
   if (!n) {
@@ -457,6 +625,10 @@ extern "C" int qb_gemm(const qb_gemm_desc* d, void* stream) {
   if (split && env_bn) bn = atoi(env_bn);
   if (d->n <= 128) bn = 128;
   const int sms = num_sms_cached();
+  // CTA pairs (256-row tiles) when they do not add row padding and the N extent fills a 256-wide tile
+  static const int pair_mode = getenv("QB_GEMM_PAIR") ? atoi(getenv("QB_GEMM_PAIR")) : 1;
+  const bool pair_ok = pair_mode && d->n >= 256 && (ceil_div(d->m_per_batch, 256) * 2 == ceil_div(d->m_per_batch, 128));
+  if (pair_ok) return split ? launch_tc2<256, 3, 3>(d, st, sms) : launch_tc2<256, 1, 6>(d, st, sms);
   if (!split) return bn == 256 ? launch_tc<256, 1, 4>(d, st, sms) : launch_tc<128, 1, 6>(d, st, sms);
   return bn == 256 ? launch_tc<256, 3, 2>(d, st, sms) : launch_tc<128, 3, 3>(d, st, sms);
 }
