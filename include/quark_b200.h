@@ -156,6 +156,14 @@ int64_t qb_lstm_workspace_bytes(int64_t B, int64_t H);
 int qb_lstm(const float* xp, const qb_half* whh_hi, const qb_half* whh_lo, int64_t B, int64_t T, int64_t H,
             qb_half* out_hi, qb_half* out_lo, void* workspace, void* stream);
 
+/* Same recurrence on tcgen05 / TMEM / TMA (the product path; lstm.cu's mma.sync version is kept as a
+ * cross-check).  whh_perm: fp16 [H/U][4U][H] with row (4j+g) of slice c = gate g of hidden unit c*U+j,
+ * U = qb_lstm_tc_units(H).  B <= 256 per call.  workspace: qb_lstm_tc_workspace_bytes(B,H). */
+int32_t qb_lstm_tc_units(int64_t H);
+int64_t qb_lstm_tc_workspace_bytes(int64_t B, int64_t H);
+int qb_lstm_tc(const float* xp, const qb_half* whh_perm, int32_t units, int64_t B, int64_t T, int64_t H,
+               qb_half* out_hi, qb_half* out_lo, void* workspace, void* stream);
+
 /* ---------------------------------------------------------------- residual vector quantiser */
 /* x [M,D] fp32, codebooks [nq,K,D] fp32 (+ their fp16 planes cb_hi/cb_lo [nq,K,D]) -> idx [M,nq] int64
  * (+ optional quantized [M,D]).  Per layer: scores |e|^2 - 2 r.e on the tensor cores (3-term split),

@@ -184,7 +184,7 @@ def test_attention(lib):
     assert e2 < 3e-3
 
 
-@pytest.mark.parametrize("B,T,H", [(2, 9, 256), (3, 20, 512), (5, 12, 1536)])
+@pytest.mark.parametrize("B,T,H", [(2, 9, 256), (3, 20, 512), (5, 12, 1536), (70, 6, 512), (130, 5, 256)])
 def test_lstm(lib, B, T, H):
     from unified_audio_b200 import ops
     k = 1.0 / math.sqrt(H)
@@ -210,6 +210,15 @@ def test_lstm(lib, B, T, H):
     ref = torch.stack(outs, 1)
     e = relerr(planes_ref(out), ref)
     print(f"lstm B{B} T{T} H{H} relerr {e:.3e}")
+    # tcgen05 version (product path)
+    U = ops.lstm_tc_units(H)
+    out2 = ops.Planes.zeros((B, T, H), True, DEV)
+    ws2 = torch.zeros(ops.lstm_tc_workspace_bytes(B, H), dtype=torch.uint8, device=DEV)
+    ops.lstm_tc(xp, ops.lstm_tc_permute(whh, U), U, B, T, H, out2, ws2)
+    torch.cuda.synchronize()
+    e2 = relerr(planes_ref(out2), ref)
+    print(f"lstm_tc B{B} T{T} H{H} U{U} relerr {e2:.3e}")
+    assert e2 < 2e-3 and relerr(planes_ref(out2)[:, 0], ref[:, 0]) < 1e-5
     assert e < 2e-3   # fp16 re-rounding of h can flip one ulp on a knife edge; exact-model error is ~1e-6
     assert relerr(planes_ref(out)[:, 0], ref[:, 0]) < 1e-5
 

@@ -123,6 +123,8 @@ class Codec(nn.Module):
 
         def transformer(prefix, n):
             layers = []
+            hdim = sd[f"{prefix}layers.0.self_attn.rnn.weight_hh_l0"].shape[1]
+            lstm_u = ops.lstm_tc_units(hdim) if hdim % 256 == 0 else 0
             for i in range(n):
                 p = f"{prefix}layers.{i}."
                 a = p + "self_attn."
@@ -132,6 +134,7 @@ class Codec(nn.Module):
                     wih=lin_w(sd[a + "rnn.weight_ih_l0"], "lstm_attn"),
                     b_ih=(sd[a + "rnn.bias_ih_l0"].float() + sd[a + "rnn.bias_hh_l0"].float()).contiguous(),
                     whh=Planes.from_f32(sd[a + "rnn.weight_hh_l0"].float().contiguous(), False),
+                    whh_perm=(ops.lstm_tc_permute(sd[a + "rnn.weight_hh_l0"], lstm_u) if lstm_u else None),
                     wqkv=lin_w(torch.cat([sd[a + f"{n_}_proj.weight"].float() for n_ in "qkv"], 0), "lstm_attn"),
                     bqkv=torch.cat([sd[a + f"{n_}_proj.bias"].float() for n_ in "qkv"], 0).contiguous(),
                     wo=lin_w(sd[a + "o_proj.weight"], "lstm_attn"),
@@ -264,14 +267,19 @@ class Codec(nn.Module):
         hid = self._planes("tf_hid", (M, I), pm)
         xp = self._buf("tf_xp", (M, 4 * C))
         qkv = self._buf("tf_qkv", (M, 3 * C))
-        ws = self._buf("lstm_ws", (ops.lstm_workspace_bytes(B, C),), torch.uint8)
+        use_tc = layers[0]["whh_perm"] is not None and B <= 256
+        ws = self._buf("lstm_ws", (max(ops.lstm_workspace_bytes(B, C), ops.lstm_tc_workspace_bytes(B, C)),), torch.uint8)
+        lstm_u = ops.lstm_tc_units(C) if use_tc else 0
         cos, sin = self._rope(F)
         att_ws = None if pa else self._buf("att_ws", (ops.attention_tc_workspace_bytes(B, F, heads),), torch.uint8)
         xm = rowmap(x, C, M, 0)
         for L in layers:
             ops.rmsnorm(x, L["in_w"], M, C, t_a)
             self._linear(t_a, L["wih"], 4 * C, M, C, bias=L["b_ih"], out_f32=rowmap(xp, 4 * C, M, 0))
-            ops.lstm(xp, L["whh"], B, F, C, t_b, ws)
+            if use_tc:
+                ops.lstm_tc(xp, L["whh_perm"], lstm_u, B, F, C, t_b, ws)
+            else:
+                ops.lstm(xp, L["whh"], B, F, C, t_b, ws)
             self._linear(t_b, L["wqkv"], 3 * C, M, C, bias=L["bqkv"], out_f32=rowmap(qkv, 3 * C, M, 0))
             if pa:   # split-precision policy: fp32 SIMT attention
                 ops.attention(qkv, B, F, heads, cos, sin, t_a)

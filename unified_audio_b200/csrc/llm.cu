@@ -280,29 +280,21 @@ struct LmGemvParams {
 template <int MODE>
 __global__ void __launch_bounds__(LM_WARPS * 32)
 lm_gemv_kernel(const LmGemvParams p) {
+  constexpr bool PAIR = MODE != LM_RESID;        // RESID: one output column per warp (more CTAs in flight)
+  constexpr int NI = LM_KT / 128;                 // float4 weight loads per lane per chunk and column
   extern __shared__ __align__(16) float xs[];   // [32][LM_KT]
   __shared__ float rstd[32];
   __shared__ float bval[LM_WARPS][32];
   __shared__ int bidx[LM_WARPS][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int B = p.B, K = p.K;
-  if (p.norm_w) {
-    for (int b = warp; b < 32; b += LM_WARPS) {
-      float q = 0.f;
-      if (b < B)
-        for (int k = lane; k < K; k += 32) { const float v = p.x[(size_t)b * K + k]; q = fmaf(v, v, q); }
-      q = warp_sum(q);
-      if (lane == 0) rstd[b] = rsqrtf(q / K + p.eps);
-    }
-  }
   int lo = 0, n_items = p.n_items;
   if (MODE == LM_HEAD) { lo = p.range[0]; n_items = (p.range[1] - lo) >> 1; }
   const int item = blockIdx.x * LM_WARPS + warp;
   const bool active = item < n_items;
-  // column pair of this warp
   int n0 = 0, n1 = 0, sec = 0, hh = 0, dd = 0;
-  const float* w0p = nullptr;
-  const float* w1p = nullptr;
+  const float* w0p = p.W;
+  const float* w1p = p.W;
   if (active) {
     if (MODE == LM_QKV) {
       dd = item & 31; hh = (item >> 5) % p.H; sec = item / (32 * p.H);
@@ -311,9 +303,34 @@ lm_gemv_kernel(const LmGemvParams p) {
     } else if (MODE == LM_GATEUP) {
       n0 = item; n1 = item;
       w0p = p.W + (size_t)item * K; w1p = p.W2 + (size_t)item * K;
+    } else if (MODE == LM_RESID) {
+      n0 = item; n1 = item;
+      w0p = p.W + (size_t)n0 * K;
     } else {
       n0 = lo + 2 * item; n1 = n0 + 1;
       w0p = p.W + (size_t)n0 * K; w1p = p.W + (size_t)n1 * K;
+    }
+  }
+  // weights of the first K chunk are fetched before anything else: their HBM/L2 latency overlaps the
+  // RMSNorm statistics and the staging of x
+  float4 wa[NI], wc[NI];
+  auto fetch = [&](int k0, float4 (&a)[NI], float4 (&c)[NI]) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int kk = k0 + i * 128 + lane * 4;
+      const bool ok = active && kk < K;
+      a[i] = ok ? __ldg(reinterpret_cast<const float4*>(w0p + kk)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (PAIR) c[i] = ok ? __ldg(reinterpret_cast<const float4*>(w1p + kk)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  fetch(0, wa, wc);
+  if (p.norm_w) {
+    for (int b = warp; b < 32; b += LM_WARPS) {
+      float q = 0.f;
+      if (b < B)
+        for (int k = lane; k < K; k += 32) { const float v = p.x[(size_t)b * K + k]; q = fmaf(v, v, q); }
+      q = warp_sum(q);
+      if (lane == 0) rstd[b] = rsqrtf(q / K + p.eps);
     }
   }
   float acc0[32], acc1[32];
@@ -335,28 +352,30 @@ lm_gemv_kernel(const LmGemvParams p) {
       *reinterpret_cast<float4*>(xs + (size_t)b * LM_KT + c4 * 4) = v;
     }
     __syncthreads();
-    if (active) {
+    float4 na[NI], nc[NI];
+    if (k0 + LM_KT < K) fetch(k0 + LM_KT, na, nc);      // next chunk's weights in flight during this chunk's FMAs
 #pragma unroll
-      for (int i = 0; i < LM_KT / 128; ++i) {
-        const int kk = i * 128 + lane * 4;
-        if (k0 + kk < K) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(w0p + k0 + kk));
-          const float4 c = __ldg(reinterpret_cast<const float4*>(w1p + k0 + kk));
+    for (int i = 0; i < NI; ++i) {
+      const int kk = i * 128 + lane * 4;
+      const float4 a = wa[i], c = wc[i];
 #pragma unroll
-          for (int b = 0; b < 32; ++b) {
-            const float4 xv = *reinterpret_cast<const float4*>(xs + (size_t)b * LM_KT + kk);
-            acc0[b] = fmaf(xv.x, a.x, fmaf(xv.y, a.y, fmaf(xv.z, a.z, fmaf(xv.w, a.w, acc0[b]))));
-            acc1[b] = fmaf(xv.x, c.x, fmaf(xv.y, c.y, fmaf(xv.z, c.z, fmaf(xv.w, c.w, acc1[b]))));
-          }
-        }
+      for (int b = 0; b < 32; ++b) {
+        const float4 xv = *reinterpret_cast<const float4*>(xs + (size_t)b * LM_KT + kk);
+        acc0[b] = fmaf(xv.x, a.x, fmaf(xv.y, a.y, fmaf(xv.z, a.z, fmaf(xv.w, a.w, acc0[b]))));
+        if (PAIR) acc1[b] = fmaf(xv.x, c.x, fmaf(xv.y, c.y, fmaf(xv.z, c.z, fmaf(xv.w, c.w, acc1[b]))));
       }
+    }
+    if (k0 + LM_KT < K) {
+#pragma unroll
+      for (int i = 0; i < NI; ++i) { wa[i] = na[i]; if (PAIR) wc[i] = nc[i]; }
     }
   }
   // lane b keeps the totals of batch row b
   float r0 = 0.f, r1 = 0.f;
 #pragma unroll
   for (int b = 0; b < 32; ++b) {
-    const float t0 = warp_sum(acc0[b]), t1 = warp_sum(acc1[b]);
+    const float t0 = warp_sum(acc0[b]);
+    const float t1 = PAIR ? warp_sum(acc1[b]) : 0.f;
     if (lane == b) { r0 = t0; r1 = t1; }
   }
   const int b = lane;
@@ -384,7 +403,6 @@ lm_gemv_kernel(const LmGemvParams p) {
   if (!active || b >= B) return;
   if (MODE == LM_RESID) {
     p.out[(size_t)b * p.N + n0] += r0;
-    p.out[(size_t)b * p.N + n1] += r1;
   } else if (MODE == LM_GATEUP) {
     p.out[(size_t)b * p.n_items + item] = silu_f(r0) * r1;
   } else {  // LM_QKV
@@ -571,13 +589,13 @@ extern "C" int qb_lm_decode_layer(float* x, int64_t B, int32_t hidden, int32_t h
                                                                               attn_buf);
   g_launches++;
   // o_proj + residual
-  p.x = attn_buf; p.K = hidden; p.W = wo; p.norm_w = nullptr; p.out = x; p.N = hidden; p.n_items = hidden / 2;
+  p.x = attn_buf; p.K = hidden; p.W = wo; p.norm_w = nullptr; p.out = x; p.N = hidden; p.n_items = hidden;
   if (int e = launch_gemv<LM_RESID>(p, p.n_items, st)) return e;
   // RMSNorm + gate/up + SwiGLU
   p.x = x; p.K = hidden; p.W = wgate; p.W2 = wup; p.norm_w = post_norm; p.out = mlp_buf; p.n_items = inter;
   if (int e = launch_gemv<LM_GATEUP>(p, p.n_items, st)) return e;
   // down + residual
-  p.x = mlp_buf; p.K = inter; p.W = wdown; p.W2 = nullptr; p.norm_w = nullptr; p.out = x; p.N = hidden; p.n_items = hidden / 2;
+  p.x = mlp_buf; p.K = inter; p.W = wdown; p.W2 = nullptr; p.norm_w = nullptr; p.out = x; p.N = hidden; p.n_items = hidden;
   if (int e = launch_gemv<LM_RESID>(p, p.n_items, st)) return e;
   QB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -13,6 +13,8 @@
 //  * cell state c stays in shared memory (fp32); h_t is published as fp16 and a grid-wide
 //    monotonic-counter barrier separates the steps.
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "quark_b200.h"
@@ -23,6 +25,7 @@ extern std::atomic<long long> g_launches;
 constexpr int LSTM_THREADS = 256;
 constexpr int LSTM_NB = 64;       // batch columns per chunk
 constexpr int LSTM_REDP = 68;     // padded row pitch (floats) of the reduction buffer
+constexpr int LSTM_REP = 1;       // replicas of the published h (spreads the all-CTA broadcast reads over L2)
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -44,7 +47,8 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
 template <int MT>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_kernel(const float* __restrict__ xp, const __half* __restrict__ whh, int B, int T, int H,
-            __half* __restrict__ out_hi, __half* __restrict__ out_lo, __half* hbuf, unsigned* counter, int Bp) {
+            __half* __restrict__ out_hi, __half* __restrict__ out_lo, __half* hbuf, unsigned* counter, int Bp,
+            long long* prof) {
   constexpr int ROWS = 16 * MT, U = 4 * MT;
   extern __shared__ __align__(16) uint8_t sm[];
   const int pitch = H + 8;  // halves; +16 B per row keeps ldmatrix conflict-free
@@ -74,7 +78,9 @@ lstm_kernel(const float* __restrict__ xp, const __half* __restrict__ whh, int B,
   const int kb32_per_q = H / 128;  // 32-wide K blocks per K quarter
   const int n_chunks = Bp / LSTM_NB;
 
+  long long pc[4] = {0, 0, 0, 0};
   for (int t = 0; t < T; ++t) {
+    long long c0 = clock64();
     if (t > 0) {  // wait until every CTA has published h_{t-1}: per-CTA flags (no atomic serialisation)
       if (warp == 0) {
         unsigned spins = 0;
@@ -87,8 +93,10 @@ lstm_kernel(const float* __restrict__ xp, const __half* __restrict__ whh, int B,
       }
       __syncthreads();
     }
-    const __half* hprev = hbuf + (size_t)((t + 1) & 1) * Bp * H;
-    __half* hcur = hbuf + (size_t)(t & 1) * Bp * H;
+    long long c1 = clock64();
+    pc[0] += c1 - c0;
+    const __half* hprev = hbuf + ((size_t)((t + 1) & 1) * LSTM_REP + (blockIdx.x % LSTM_REP)) * Bp * H;
+    __half* hcur = hbuf + (size_t)(t & 1) * LSTM_REP * Bp * H;
 
     for (int ch = 0; ch < n_chunks; ++ch) {
       const int nb0 = ch * LSTM_NB;
@@ -151,6 +159,8 @@ lstm_kernel(const float* __restrict__ xp, const __half* __restrict__ whh, int B,
           }
         }
       }
+      long long c2 = clock64();
+      pc[1] += c2 - c1;
       // ---- K-quarter partials -> smem
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
@@ -183,7 +193,8 @@ lstm_kernel(const float* __restrict__ xp, const __half* __restrict__ whh, int B,
           const float h = og * tanhf(c);
           __half hh, hl;
           split_f16(h, hh, hl);
-          hcur[(size_t)n * H + u0 + j] = hh;
+#pragma unroll
+          for (int rp = 0; rp < LSTM_REP; ++rp) hcur[((size_t)rp * Bp + n) * H + u0 + j] = hh;
           if (n < B) {
             const long long o = ((long long)n * T + t) * H + u0 + j;
             out_hi[o] = hh;
@@ -192,12 +203,19 @@ lstm_kernel(const float* __restrict__ xp, const __half* __restrict__ whh, int B,
         }
       }
       __syncthreads();  // red / cs reuse by the next chunk
+      c1 = clock64();
+      pc[2] += c1 - c2;
     }
     // ---- publish h_t
     if (tid == 0) {
       __threadfence();
       asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(counter + blockIdx.x), "r"((unsigned)(t + 1)) : "memory");
     }
+    pc[3] += clock64() - c1;
+  }
+  if (prof && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+    const int o = blockIdx.x == 0 ? 0 : 4;
+    for (int i = 0; i < 4; ++i) prof[o + i] = pc[i];
   }
 }
 
@@ -214,7 +232,7 @@ using namespace qb;
 
 extern "C" int64_t qb_lstm_workspace_bytes(int64_t B, int64_t H) {
   const int64_t Bp = ceil_div(B, LSTM_NB) * LSTM_NB;
-  return 2 * Bp * H * 2 + 4096;
+  return 2 * LSTM_REP * Bp * H * 2 + 4096;
 }
 
 extern "C" int qb_lstm(const float* xp, const qb_half* whh_hi, const qb_half* whh_lo, int64_t B, int64_t T, int64_t H,
@@ -234,15 +252,24 @@ extern "C" int qb_lstm(const float* xp, const qb_half* whh_hi, const qb_half* wh
   QB_REQUIRE(smem <= 227 * 1024, "lstm: shared memory budget exceeded (%zu bytes; B too large?)", smem);
   QB_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)qb_lstm_workspace_bytes(B, H), st));
   __half* hbuf = (__half*)workspace;
-  unsigned* counter = (unsigned*)((uint8_t*)workspace + (size_t)2 * Bp * H * 2);
+  unsigned* counter = (unsigned*)((uint8_t*)workspace + (size_t)2 * LSTM_REP * Bp * H * 2);
   const __half* w = (const __half*)whh_hi;
   __half* oh = (__half*)out_hi;
   __half* ol = (__half*)out_lo;
   int Bi = (int)B, Ti = (int)T, Hi = (int)H, Bpi = Bp;
-  void* args[] = {&xp, &w, &Bi, &Ti, &Hi, &oh, &ol, &hbuf, &counter, &Bpi};
+  static long long* prof = nullptr;
+  if (!prof && getenv("QB_LSTM_PROF")) cudaMalloc(&prof, 64);
+  void* args[] = {&xp, &w, &Bi, &Ti, &Hi, &oh, &ol, &hbuf, &counter, &Bpi, &prof};
   const void* fn = mt == 1 ? (const void*)lstm_kernel<1> : mt == 2 ? (const void*)lstm_kernel<2> : (const void*)lstm_kernel<3>;
   QB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   QB_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LSTM_THREADS), args, smem, st));
   g_launches++;
+  if (prof) {
+    long long h[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, prof, 64, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[lstm prof] T=%d cycles/step cta0: wait %.0f mma %.0f reduce+pointwise %.0f publish %.0f | ctaN: wait %.0f mma %.0f rp %.0f pub %.0f\n", Ti,
+            h[0] / (double)Ti, h[1] / (double)Ti, h[2] / (double)Ti, h[3] / (double)Ti, h[4] / (double)Ti, h[5] / (double)Ti, h[6] / (double)Ti, h[7] / (double)Ti);
+  }
   return 0;
 }

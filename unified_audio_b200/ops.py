@@ -164,6 +164,26 @@ def lstm(xp, whh: Planes, B, T, H, out: Planes, workspace):
     _lib.check(_lib.load().qb_lstm(_p(xp), _p(whh.hi), None, B, T, H, _p(out.hi), _p(out.lo), _p(workspace), _stream()))
 
 
+def lstm_tc_units(H):
+    return int(_lib.load().qb_lstm_tc_units(H))
+
+
+def lstm_tc_workspace_bytes(B, H):
+    return int(_lib.load().qb_lstm_tc_workspace_bytes(B, H))
+
+
+def lstm_tc_permute(whh: torch.Tensor, U: int) -> torch.Tensor:
+    """[4H,H] (gate-major i|f|g|o) -> fp16 [H/U][4U][H], row 4j+g of slice c = gate g of unit c*U+j."""
+    H = whh.shape[1]
+    rows = (torch.arange(4, device=whh.device)[None, None, :] * H +
+            torch.arange(H, device=whh.device).reshape(H // U, U)[:, :, None]).reshape(-1)
+    return whh.float().clamp(-65504.0, 65504.0)[rows].half().contiguous()
+
+
+def lstm_tc(xp, whh_perm, U, B, T, H, out: Planes, workspace):
+    _lib.check(_lib.load().qb_lstm_tc(_p(xp), _p(whh_perm), U, B, T, H, _p(out.hi), _p(out.lo), _p(workspace), _stream()))
+
+
 def rvq_workspace_bytes(M, D, K):
     return int(_lib.load().qb_rvq_workspace_bytes(M, D, K))
 
