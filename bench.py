@@ -310,6 +310,8 @@ def main():
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     peaks = load_peaks()
@@ -427,7 +429,7 @@ def main():
         gpu_launches=int(launches),
         clocks=clocks,
         roofline=dict(bound="tensor", achieved=gemm_tf, peak=peaks["tf_burst"], unit="TFLOP/s", frac=gemm_tf / peaks["tf_burst"],
-                      traffic=traffic, kernel="gemm_tc_kernel<256,1,4> ConvNeXt pwconv1 [32000x4608x1536] fp16, timed alone",
+                      traffic=traffic, kernel="gemm_tc2_kernel<256,1,6> (cta_group::2) ConvNeXt pwconv1 [32000x4608x1536] fp16 + GELU epilogue, timed alone",
                       peak_source=f"{peaks['src']} dense bf16 burst (fp16 shares the pipe)",
                       path_algorithmic_tflops=path_tf, path_frac_of_sustained=path_tf / peaks["tf_sus"]),
     )
