@@ -133,16 +133,27 @@ int qb_stft_post(const float* spec, int64_t ld_spec, int64_t B, int64_t frames, 
  * im = ...*sin(p)   (vq/heads.py:55-65). */
 int qb_istft_pre(const float* head, int64_t ld_in, int64_t M, int32_t nf, qb_half* hi, qb_half* lo, int64_t ld,
                  void* stream);
-/* windowed frames [B, F, n_fft] fp32 -> overlap-add (hop = n_fft/2), trim, / window envelope
+/* windowed frames [B, F, n_fft] fp32 -> overlap-add (n_fft a multiple of hop), trim, / window envelope
  * -> wav [B, F*hop]   (vq/spectral_ops.py:56-73). */
-int qb_istft_ola(const float* frames, const float* window, int64_t B, int64_t F, int32_t n_fft, float* wav,
-                 void* stream);
+int qb_istft_ola(const float* frames, const float* window, int64_t B, int64_t F, int32_t n_fft, int32_t hop,
+                 float* wav, void* stream);
+/* Reflect padding of SConv1d (HCodec-1.0/vq/encoder_modules/conv.py:79-96,196-210): mirror-fill pad_l rows
+ * before and pad_r rows after the T interior rows (starting at row_off) of a padded plane buffer. */
+int qb_reflect_pad_rows(qb_half* hi, qb_half* lo, int64_t B, int64_t rows_per_batch, int64_t ld, int64_t T,
+                        int64_t row_off, int32_t pad_l, int32_t pad_r, void* stream);
+/* Depthwise conv over time, odd k, zero 'same' padding, channel-last fp32; w [C,k]
+ * (sub-pixel up-sampler's dw conv, HCodec-1.0/vq/conv.py:84-92). */
+int qb_dwconv(const float* x, const float* w, const float* bias, int64_t B, int64_t T, int64_t C, int32_t k,
+              float* out, void* stream);
 
 /* ---------------------------------------------------------------- sequence ops */
 /* Non-causal multi-head attention with RoPE applied to q,k on load
  * (encoder_modules/transformer.py:134-182).  qkv [B,T,3*H*D] fp32 (q|k|v), D = 64.  Output planes. */
 int qb_attention(const float* qkv, int64_t B, int64_t T, int32_t heads, const float* rope_cos,
                  const float* rope_sin, qb_half* out_hi, qb_half* out_lo, void* stream);
+/* fp32 SIMT attention for head_dim 64 or 96 (H-Codec-1.0's decoder transformer: 768 / 8 heads). */
+int qb_attention_hd(const float* qkv, int64_t B, int64_t T, int32_t heads, int32_t head_dim, const float* rope_cos,
+                    const float* rope_sin, qb_half* out_hi, qb_half* out_lo, void* stream);
 /* Same attention on the tensor cores (mma.sync m16n8k16): q,k,v rounded to fp16 after RoPE, fp32
  * softmax / accumulation - the single-pass fp16 precision class.  workspace:
  * qb_attention_tc_workspace_bytes(B,T,heads). */
@@ -194,7 +205,10 @@ int qb_lm_flash_attn(const float* q32, const float* k_cache, const float* v_cach
                      int32_t heads, int32_t pos0, int32_t Lmax, qb_half* out_hi, qb_half* out_lo, void* stream);
 /* One decoder layer for ONE new token per sequence (B <= 32), fp32 weights streamed once:
  * x [B,hidden] updated in place; K/V appended at *pos (device int, not modified here).
- * wqkv = [q;k;v] rows [3*hidden, hidden]; scratch q_buf/attn_buf [B,hidden], mlp_buf [B,inter]. */
+ * wqkv = [q;k;v] rows [3*hidden, hidden]; scratch q_buf/attn_buf [B,hidden], mlp_buf [B,inter].
+ * The RMSNorm weights must be FOLDED into the following projection by the caller (wqkv' = wqkv diag(in_norm),
+ * wgate' / wup' likewise with post_norm): the kernels apply only the per-row 1/rms.  in_norm / post_norm are
+ * passed as non-NULL flags that the normalisation is wanted. */
 int qb_lm_decode_layer(float* x, int64_t B, int32_t hidden, int32_t heads, int32_t inter, const float* in_norm,
                        const float* wqkv, const float* wo, const float* post_norm, const float* wgate,
                        const float* wup, const float* wdown, float* k_cache, float* v_cache, int32_t Lmax,
@@ -203,6 +217,7 @@ int qb_lm_decode_layer(float* x, int64_t B, int32_t hidden, int32_t heads, int32
 /* Final RMSNorm + output head restricted to columns [range[0], range[1]) (device ints; llm_sft.py:148-153)
  * + greedy arg-max (llm.py:286-287, do_sample=False) -> out_ids[b*out_stride + slot[0]]; x_next[b] =
  * embedding[token]; then slot[0]++ and *pos++ (slot is int32[2], second word is scratch).
+ * w_head must have final_norm folded in (w_head' = w_head diag(final_norm)).
  * part_val/part_idx: scratch [max_cols/16 * 32]. */
 int qb_lm_head_argmax(const float* x, int64_t B, int32_t hidden, const float* final_norm, const float* w_head,
                       const int32_t* range, int32_t max_cols, const float* embedding, float* x_next,

@@ -99,9 +99,11 @@ def rms_norm(w, x, eps=1e-6):
     return F.rms_norm(x, (x.shape[-1],), w, eps)
 
 
-def transformer_layer(sd, p, x, head_dim=64, aten_lstm=True):
+def transformer_layer(sd, p, x, head_dim=64, aten_lstm=True, num_heads=None):
     """transformer.py:367-393 (layer), :120-182 (attention), :218-226 (MLP).  x [B,T,C]."""
     B, T, C = x.shape
+    if num_heads is not None:
+        head_dim = C // num_heads
     nh = C // head_dim
     h = rms_norm(sd[p + "input_layernorm.weight"], x)
     h = (lstm_layer_aten if aten_lstm else lstm_layer)(sd, p + "self_attn.rnn.", h)
@@ -121,7 +123,7 @@ def transformer_layer(sd, p, x, head_dim=64, aten_lstm=True):
     return x + h
 
 
-def transformer(sd, p, x_btc, n_layers, **kw):
+def transformer(sd, p, x_btc, n_layers, **kw):  # kw: aten_lstm, num_heads / head_dim
     """transformer.py:449-489, non-causal (mask None), no final norm."""
     for i in range(n_layers):
         x_btc = transformer_layer(sd, f"{p}layers.{i}.", x_btc, **kw)

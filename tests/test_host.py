@@ -39,6 +39,28 @@ def test_oracle_reproduces_reference_golden(name):
     assert rec.shape[-1] == meta["n_tokens"] * 3840      # decode(encode(x)) length (SURVEY 8c self-check)
 
 
+def test_oracle_h1_reproduces_reference_golden():
+    """H-Codec-1.0 (BASELINE configs[0]): 1 s 16 kHz clip; golden = outputs of the reference's own Codec."""
+    from oracle import hcodec1
+    z = np.load(os.path.join(GOLD, "h1_full_1s.npz"))
+    meta = json.loads(str(z["meta"]))
+    c = hcodec1.H1
+    sd = hcodec1.make_state_dict(c, meta["seed_w"])
+    g = torch.Generator().manual_seed(meta["seed_x"])
+    x = 0.1 * torch.randn(1, 1, 16000, generator=g)
+    g2 = torch.Generator().manual_seed(meta["seed_x"] + 1)
+    f = torch.randn(1, 768, 50, generator=g2)
+    feat = torch.sign(f) * f.abs() ** 0.3
+    ac, sc = hcodec1.codec_encode(sd, c, x, feat)
+    rec = hcodec1.codec_decode(sd, c, ac, sc)
+    assert torch.equal(ac, torch.from_numpy(z["acoustic_codes"])) and torch.equal(sc, torch.from_numpy(z["semantic_codes"]))
+    assert float((rec - torch.from_numpy(z["wav_rec"])).abs().max()) < 1e-6 and rec.shape == (1, 16000)
+    from unified_audio_b200.codec_h1 import CodecH1
+    ref = json.load(open(os.path.join(GOLD, "h1_keys.json")))
+    mine = {k: list(v.shape) for k, v in CodecH1({}, {}, {}).state_dict().items()}
+    assert mine == {k: v for k, v in ref.items() if not k.startswith("semantic_decoder.")}
+
+
 def test_oracle_rvq_self_checks():
     """get_output_from_indices(indices) == returned quantized bit-for-bit; fp64 audit agrees on safe margins;
     explicit-recurrence LSTM == ATen LSTM."""

@@ -9,5 +9,6 @@ Kernels live in csrc/ behind the C ABI of include/quark_b200.h (lib/libquark_b20
 __version__ = "0.1.0"
 
 from .codec import Codec  # noqa: E402,F401
+from .codec_h1 import CodecH1  # noqa: E402,F401
 from .rvq import ResidualVQ  # noqa: E402,F401
 from .llm import LLM_SFT  # noqa: E402,F401

@@ -49,7 +49,10 @@ SIGNATURES = {
     "qb_wav_to_hopblocks": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp]),
     "qb_stft_post": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _i64, _i64, _i64, _vp]),
     "qb_istft_pre": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _vp]),
-    "qb_istft_ola": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp]),
+    "qb_istft_ola": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
+    "qb_reflect_pad_rows": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _vp]),
+    "qb_dwconv": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp]),
+    "qb_attention_hd": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "qb_attention": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "qb_attention_tc_workspace_bytes": (C.c_int64, [_i64, _i64, _i32]),
     "qb_attention_tc": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -231,7 +231,7 @@ class Codec(nn.Module):
         return p
 
     def _rope(self, T, D=64):
-        key = ("rope", T)
+        key = ("rope", T, D)
         r = self._ws.get(key)
         if r is None:
             inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2, dtype=torch.int64).float() / D))
@@ -257,9 +257,11 @@ class Codec(nn.Module):
             self._linear(t1, blk["w1"], I, M, C, bias=blk["b1"], act=ACT_GELU, out_planes=hid, out_planes_map=(I, M, 0))
             self._linear(hid, blk["w2"], C, M, I, bias=blk["b2"], gamma=blk["gamma"], residual=xm, out_f32=xm)
 
-    def _transformer(self, layers, x, B, F, C):
+    def _transformer(self, layers, x, B, F, C, heads=None):
         """encoder_modules/transformer.py:367-393 per layer; x [B*F, C] fp32 updated in place."""
-        M, heads, I = B * F, C // 64, min(4 * C, 4096)
+        heads = heads or C // 64
+        hd = C // heads
+        M, I = B * F, min(4 * C, 4096)
         pa, pm = self.policy["lstm_attn"], self.policy["mlp"]
         t_a = self._planes("tf_a", (M, C), pa)
         t_b = self._planes("tf_b", (M, C), pa)
@@ -270,8 +272,9 @@ class Codec(nn.Module):
         use_tc = layers[0]["whh_perm"] is not None and B <= 256
         ws = self._buf("lstm_ws", (max(ops.lstm_workspace_bytes(B, C), ops.lstm_tc_workspace_bytes(B, C)),), torch.uint8)
         lstm_u = ops.lstm_tc_units(C) if use_tc else 0
-        cos, sin = self._rope(F)
-        att_ws = None if pa else self._buf("att_ws", (ops.attention_tc_workspace_bytes(B, F, heads),), torch.uint8)
+        cos, sin = self._rope(F, hd)
+        tc_att = (not pa) and hd == 64
+        att_ws = self._buf("att_ws", (ops.attention_tc_workspace_bytes(B, F, heads),), torch.uint8) if tc_att else None
         xm = rowmap(x, C, M, 0)
         for L in layers:
             ops.rmsnorm(x, L["in_w"], M, C, t_a)
@@ -281,10 +284,10 @@ class Codec(nn.Module):
             else:
                 ops.lstm(xp, L["whh"], B, F, C, t_b, ws)
             self._linear(t_b, L["wqkv"], 3 * C, M, C, bias=L["bqkv"], out_f32=rowmap(qkv, 3 * C, M, 0))
-            if pa:   # split-precision policy: fp32 SIMT attention
-                ops.attention(qkv, B, F, heads, cos, sin, t_a)
-            else:    # single-pass fp16 policy: tensor-core flash attention
+            if tc_att:   # single-pass fp16 policy, head_dim 64: tensor-core flash attention
                 ops.attention_tc(qkv, B, F, heads, cos, sin, t_a, att_ws)
+            else:        # split-precision policy or head_dim 96: fp32 SIMT attention
+                ops.attention_hd(qkv, B, F, heads, hd, cos, sin, t_a)
             self._linear(t_a, L["wo"], C, M, C, residual=xm, out_f32=xm)
             ops.rmsnorm(x, L["post_w"], M, C, t_m)
             self._linear(t_m, L["w13"], 2 * I, M, C, act=ACT_SWIGLU, out_planes=hid, out_planes_map=(I, M, 0))
@@ -451,7 +454,7 @@ class Codec(nn.Module):
         frames = self._buf("dec_frames", (M, n_fft))
         self._linear(sp, W["dft_inv"], n_fft, M, g["kin"], out_f32=rowmap(frames, n_fft, M, 0))
         wav = torch.empty(B, F * hop, device=z.device)
-        ops.istft_ola(frames, W["istft_window"], B, F, n_fft, wav)
+        ops.istft_ola(frames, W["istft_window"], B, F, n_fft, wav, hop)
         return wav
 
     # ------------------------------------------------------------------ public surface

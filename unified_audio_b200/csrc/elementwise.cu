@@ -321,26 +321,54 @@ __global__ void istft_pre_kernel(const float* __restrict__ head, long long ld_in
 }
 
 __global__ void istft_ola_kernel(const float* __restrict__ frames, const float* __restrict__ window, int F, int n_fft,
-                                 float* __restrict__ wav) {
-  const int hop = n_fft / 2, pad = (n_fft - hop) / 2;
+                                 int hop, float* __restrict__ wav) {
+  const int pad = (n_fft - hop) / 2, R = n_fft / hop;
   const int b = blockIdx.y;
   const long long len = (long long)F * hop;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= len) return;
   const long long u = t + pad;
-  const int f1 = (int)(u / hop), f0 = f1 - 1;
+  const int f_hi = (int)(u / hop);
   float acc = 0.f, env = 0.f;
-  if (f0 >= 0 && f0 < F) {
-    int i = (int)(u - (long long)f0 * hop);
-    acc += frames[((long long)b * F + f0) * n_fft + i];
-    env += window[i] * window[i];
-  }
-  if (f1 < F) {
-    int i = (int)(u - (long long)f1 * hop);
-    acc += frames[((long long)b * F + f1) * n_fft + i];
-    env += window[i] * window[i];
+  for (int r = R - 1; r >= 0; --r) {       // frames in increasing order f_hi-R+1 .. f_hi (fold's accumulation order)
+    const int f = f_hi - r;
+    if (f >= 0 && f < F) {
+      const int i = (int)(u - (long long)f * hop);
+      acc += frames[((long long)b * F + f) * n_fft + i];
+      env += window[i] * window[i];
+    }
   }
   wav[(long long)b * len + t] = acc / env;
+}
+
+// mirror-fill the pad rows of a channel-last padded plane buffer (reflect padding of SConv1d,
+// HCodec-1.0/vq/encoder_modules/conv.py:79-96,196-210): row off-i <- row off+i, row off+T-1+i <- row off+T-1-i
+__global__ void reflect_pad_rows_kernel(__half* __restrict__ hi, __half* __restrict__ lo, long long rpb, long long ld,
+                                        int T, int off, int pad_l, int pad_r) {
+  const int b = blockIdx.y, pr = blockIdx.x;          // pr < pad_l: left rows, else right rows
+  long long dst, src;
+  if (pr < pad_l) { dst = off - 1 - pr; src = off + 1 + pr; }
+  else { const int i = pr - pad_l; dst = off + T + i; src = off + T - 2 - i; }
+  const long long d = ((long long)b * rpb + dst) * ld, s2 = ((long long)b * rpb + src) * ld;
+  for (int c = threadIdx.x; c < ld / 8; c += blockDim.x) {
+    reinterpret_cast<uint4*>(hi + d)[c] = reinterpret_cast<const uint4*>(hi + s2)[c];
+    if (lo) reinterpret_cast<uint4*>(lo + d)[c] = reinterpret_cast<const uint4*>(lo + s2)[c];
+  }
+}
+
+// depthwise conv over time, odd kernel k, zero 'same' padding, channel-last fp32 (sub-pixel up-sampler's dw conv,
+// vq/conv.py:84-92).  w [C,k].
+__global__ void dwconv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                              int T, int C, int k, float* __restrict__ out) {
+  const int t = blockIdx.x, b = blockIdx.y, h = k / 2;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = bias ? bias[c] : 0.f;
+    for (int j = 0; j < k; ++j) {
+      const int tt = t + j - h;
+      if (tt >= 0 && tt < T) acc = fmaf(w[(long long)c * k + j], x[((long long)b * T + tt) * C + c], acc);
+    }
+    out[((long long)b * T + t) * C + c] = acc;
+  }
 }
 
 }  // namespace qb
@@ -464,10 +492,30 @@ extern "C" int qb_istft_pre(const float* head, int64_t ld_in, int64_t M, int32_t
   QB_LAUNCH_END();
 }
 
-extern "C" int qb_istft_ola(const float* frames, const float* window, int64_t B, int64_t F, int32_t n_fft, float* wav,
-                            void* stream) {
-  QB_REQUIRE(frames && window && wav && n_fft % 4 == 0, "istft_ola: bad args");
-  dim3 grid((unsigned)ceil_div(F * (n_fft / 2), 256), (unsigned)B);
-  istft_ola_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames, window, (int)F, n_fft, wav);
+extern "C" int qb_istft_ola(const float* frames, const float* window, int64_t B, int64_t F, int32_t n_fft, int32_t hop,
+                            float* wav, void* stream) {
+  QB_REQUIRE(frames && window && wav && hop > 0 && n_fft % hop == 0 && (n_fft - hop) % 2 == 0, "istft_ola: bad args");
+  dim3 grid((unsigned)ceil_div(F * hop, 256), (unsigned)B);
+  istft_ola_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames, window, (int)F, n_fft, hop, wav);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_reflect_pad_rows(qb_half* hi, qb_half* lo, int64_t B, int64_t rows_per_batch, int64_t ld, int64_t T,
+                                   int64_t row_off, int32_t pad_l, int32_t pad_r, void* stream) {
+  QB_REQUIRE(hi && ld % 8 == 0 && pad_l >= 0 && pad_r >= 0 && row_off >= pad_l && row_off + T + pad_r <= rows_per_batch,
+             "reflect_pad_rows: bad args");
+  QB_REQUIRE(T > pad_l && T > pad_r, "reflect_pad_rows: input shorter than the reflection");
+  if (pad_l + pad_r == 0) return 0;
+  dim3 grid((unsigned)(pad_l + pad_r), (unsigned)B);
+  reflect_pad_rows_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((__half*)hi, (__half*)lo, rows_per_batch, ld, (int)T,
+                                                                 (int)row_off, pad_l, pad_r);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_dwconv(const float* x, const float* w, const float* bias, int64_t B, int64_t T, int64_t C, int32_t k,
+                         float* out, void* stream) {
+  QB_REQUIRE(x && w && out && k % 2 == 1, "dwconv: bad args");
+  dim3 grid((unsigned)T, (unsigned)B);
+  dwconv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, (int)T, (int)C, k, out);
   QB_LAUNCH_END();
 }

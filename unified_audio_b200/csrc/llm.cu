@@ -277,13 +277,17 @@ struct LmGemvParams {
   int* part_idx;
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(LM_WARPS * 32)
+// RMSNorm is applied algebraically: the norm weight g is folded into the projection weights on the host
+// (W' = W diag(g)), so  (x * rstd * g) . W^T  ==  rstd * (x . W'^T)  and the per-row rstd only scales the
+// finished dot products - the raw x is staged with cp.async while the weight rows stream in, and the
+// sum of squares is taken from the staged tile after the FMAs (nothing serialises in front of the loads).
+template <int MODE, bool MULTI>
+__global__ void __launch_bounds__(LM_WARPS * 32, MULTI ? 1 : 2)
 lm_gemv_kernel(const LmGemvParams p) {
   constexpr bool PAIR = MODE != LM_RESID;        // RESID: one output column per warp (more CTAs in flight)
   constexpr int NI = LM_KT / 128;                 // float4 weight loads per lane per chunk and column
   extern __shared__ __align__(16) float xs[];   // [32][LM_KT]
-  __shared__ float rstd[32];
+  __shared__ float ssq[32];
   __shared__ float bval[LM_WARPS][32];
   __shared__ int bidx[LM_WARPS][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -311,8 +315,19 @@ lm_gemv_kernel(const LmGemvParams p) {
       w0p = p.W + (size_t)n0 * K; w1p = p.W + (size_t)n1 * K;
     }
   }
-  // weights of the first K chunk are fetched before anything else: their HBM/L2 latency overlaps the
-  // RMSNorm statistics and the staging of x
+  auto stage_x = [&](int k0) {   // asynchronous global -> shared copy of x[:, k0 : k0 + LM_KT]
+    for (int e = tid; e < 32 * (LM_KT / 4); e += LM_WARPS * 32) {
+      const int b = e / (LM_KT / 4), c4 = e - b * (LM_KT / 4);
+      float* dst = xs + (size_t)b * LM_KT + c4 * 4;
+      if (b < B && k0 + c4 * 4 < K) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(p.x + (size_t)b * K + k0 + c4 * 4)
+                     : "memory");
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   float4 wa[NI], wc[NI];
   auto fetch = [&](int k0, float4 (&a)[NI], float4 (&c)[NI]) {
 #pragma unroll
@@ -323,37 +338,17 @@ lm_gemv_kernel(const LmGemvParams p) {
       if (PAIR) c[i] = ok ? __ldg(reinterpret_cast<const float4*>(w1p + kk)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
+  stage_x(0);
   fetch(0, wa, wc);
-  if (p.norm_w) {
-    for (int b = warp; b < 32; b += LM_WARPS) {
-      float q = 0.f;
-      if (b < B)
-        for (int k = lane; k < K; k += 32) { const float v = p.x[(size_t)b * K + k]; q = fmaf(v, v, q); }
-      q = warp_sum(q);
-      if (lane == 0) rstd[b] = rsqrtf(q / K + p.eps);
-    }
-  }
+  if (tid < 32) ssq[tid] = 0.f;
   float acc0[32], acc1[32];
 #pragma unroll
   for (int b = 0; b < 32; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
   for (int k0 = 0; k0 < K; k0 += LM_KT) {
-    __syncthreads();
-    for (int e = tid; e < 32 * (LM_KT / 4); e += LM_WARPS * 32) {
-      const int b = e / (LM_KT / 4), c4 = e - b * (LM_KT / 4);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b < B && k0 + c4 * 4 < K) {
-        v = *reinterpret_cast<const float4*>(p.x + (size_t)b * K + k0 + c4 * 4);
-        if (p.norm_w) {
-          const float4 g = *reinterpret_cast<const float4*>(p.norm_w + k0 + c4 * 4);
-          const float r = rstd[b];
-          v.x *= r * g.x; v.y *= r * g.y; v.z *= r * g.z; v.w *= r * g.w;
-        }
-      }
-      *reinterpret_cast<float4*>(xs + (size_t)b * LM_KT + c4 * 4) = v;
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     float4 na[NI], nc[NI];
-    if (k0 + LM_KT < K) fetch(k0 + LM_KT, na, nc);      // next chunk's weights in flight during this chunk's FMAs
+    if (MULTI && k0 + LM_KT < K) fetch(k0 + LM_KT, na, nc);      // next chunk's weights in flight
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
       const int kk = i * 128 + lane * 4;
@@ -365,7 +360,21 @@ lm_gemv_kernel(const LmGemvParams p) {
         if (PAIR) acc1[b] = fmaf(xv.x, c.x, fmaf(xv.y, c.y, fmaf(xv.z, c.z, fmaf(xv.w, c.w, acc1[b]))));
       }
     }
-    if (k0 + LM_KT < K) {
+    if (p.norm_w) {   // sum of squares of the staged rows (rows warp, warp+8, ...)
+      for (int b = warp; b < B; b += LM_WARPS) {
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < LM_KT / 128; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(xs + (size_t)b * LM_KT + i * 128 + lane * 4);
+          q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
+        }
+        q = warp_sum(q);
+        if (lane == 0) ssq[b] += q;
+      }
+    }
+    if (MULTI && k0 + LM_KT < K) {
+      __syncthreads();                 // everyone is done with this chunk of xs
+      stage_x(k0 + LM_KT);
 #pragma unroll
       for (int i = 0; i < NI; ++i) { wa[i] = na[i]; if (PAIR) wc[i] = nc[i]; }
     }
@@ -379,6 +388,12 @@ lm_gemv_kernel(const LmGemvParams p) {
     if (lane == b) { r0 = t0; r1 = t1; }
   }
   const int b = lane;
+  if (p.norm_w) {
+    __syncthreads();
+    const float rs = rsqrtf(ssq[b] / K + p.eps);
+    r0 *= rs;
+    r1 *= rs;
+  }
   if (MODE == LM_HEAD) {
     float bv = -INFINITY;
     int bi = 0x7fffffff;
@@ -550,18 +565,22 @@ extern "C" int qb_lm_flash_attn(const float* q32, const float* k_cache, const fl
   return 0;
 }
 
-template <int MODE>
-static int launch_gemv(const LmGemvParams& p, int n_items_max, cudaStream_t st) {
+template <int MODE, bool MULTI>
+static int launch_gemv_t(const LmGemvParams& p, int n_items_max, cudaStream_t st) {
   static bool set = false;
   const size_t smem = (size_t)32 * LM_KT * sizeof(float);
   if (!set) {
-    QB_CHECK_CUDA(cudaFuncSetAttribute(lm_gemv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QB_CHECK_CUDA(cudaFuncSetAttribute(lm_gemv_kernel<MODE, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     set = true;
   }
-  lm_gemv_kernel<MODE><<<(unsigned)ceil_div(n_items_max, LM_WARPS), LM_WARPS * 32, smem, st>>>(p);
+  lm_gemv_kernel<MODE, MULTI><<<(unsigned)ceil_div(n_items_max, LM_WARPS), LM_WARPS * 32, smem, st>>>(p);
   g_launches++;
   QB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+template <int MODE>
+static int launch_gemv(const LmGemvParams& p, int n_items_max, cudaStream_t st) {
+  return p.K > LM_KT ? launch_gemv_t<MODE, true>(p, n_items_max, st) : launch_gemv_t<MODE, false>(p, n_items_max, st);
 }
 
 extern "C" int qb_lm_decode_layer(float* x, int64_t B, int32_t hidden, int32_t heads, int32_t inter, const float* in_norm,

@@ -119,13 +119,17 @@ class LLM_SFT(nn.Module):
                 wqkv=Planes.from_f32(wqkv, True), wo=Planes.from_f32(sd[p + "self_attn.o_proj.weight"], True),
                 wgu=Planes.from_f32(torch.stack([wg, wu], 1).reshape(-1, self.hidden), True),
                 wd=Planes.from_f32(sd[p + "mlp.down_proj.weight"], True),
-                wqkv32=wqkv, wo32=sd[p + "self_attn.o_proj.weight"].contiguous(), wg32=wg, wu32=wu,
+                # decode path: fp32 weights with the preceding RMSNorm weight folded in (W' = W diag(g))
+                wqkv32=(wqkv * sd[p + "input_layernorm.weight"][None, :]).contiguous(),
+                wo32=sd[p + "self_attn.o_proj.weight"].contiguous(),
+                wg32=(wg * sd[p + "post_attention_layernorm.weight"][None, :]).contiguous(),
+                wu32=(wu * sd[p + "post_attention_layernorm.weight"][None, :]).contiguous(),
                 wd32=sd[p + "mlp.down_proj.weight"].contiguous()))
         inv = 1.0 / (10000.0 ** (torch.arange(0, 64, 2, dtype=torch.int64).float() / 64))
         fr = torch.arange(self.max_pos).float()[:, None] * inv[None, :]
         emb = torch.cat((fr, fr), -1)
         self._w = dict(layers=layers, norm=sd["norm.weight"].contiguous(), head=Planes.from_f32(sd["output_head.weight"], True),
-                       head32=sd["output_head.weight"].contiguous(), emb=sd["codec_embedding.weight"].contiguous(),
+                       head32=(sd["output_head.weight"] * sd["norm.weight"][None, :]).contiguous(), emb=sd["codec_embedding.weight"].contiguous(),
                        adapter=Planes.from_f32(sd["adapter.weight"], True), adapter_b=sd["adapter.bias"].contiguous(),
                        cos=emb.cos().to(dev).contiguous(), sin=emb.sin().to(dev).contiguous())
         return self._w

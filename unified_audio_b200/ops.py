@@ -138,8 +138,23 @@ def istft_pre(head, ld_in, M, nf, out: Planes, ld):
     _lib.check(_lib.load().qb_istft_pre(_p(head), ld_in, M, nf, _p(out.hi), _p(out.lo), ld, _stream()))
 
 
-def istft_ola(frames, window, B, F, n_fft, wav):
-    _lib.check(_lib.load().qb_istft_ola(_p(frames), _p(window), B, F, n_fft, _p(wav), _stream()))
+def istft_ola(frames, window, B, F, n_fft, wav, hop=None):
+    _lib.check(_lib.load().qb_istft_ola(_p(frames), _p(window), B, F, n_fft, hop if hop is not None else n_fft // 2, _p(wav),
+                                        _stream()))
+
+
+def reflect_pad_rows(buf: Planes, B, rows_per_batch, ld, T, row_off, pad_l, pad_r):
+    _lib.check(_lib.load().qb_reflect_pad_rows(_p(buf.hi), _p(buf.lo), B, rows_per_batch, ld, T, row_off, pad_l, pad_r,
+                                               _stream()))
+
+
+def dwconv(x, w, bias, B, T, Cc, k, out):
+    _lib.check(_lib.load().qb_dwconv(_p(x), _p(w), _p(bias), B, T, Cc, k, _p(out), _stream()))
+
+
+def attention_hd(qkv, B, T, heads, head_dim, rope_cos, rope_sin, out: Planes):
+    _lib.check(_lib.load().qb_attention_hd(_p(qkv), B, T, heads, head_dim, _p(rope_cos), _p(rope_sin), _p(out.hi), _p(out.lo),
+                                           _stream()))
 
 
 def attention(qkv, B, T, heads, rope_cos, rope_sin, out: Planes):
