@@ -4,11 +4,16 @@
 // Measured (profiles/): the mma.sync version (lstm.cu) spends 15.4k of its 26k cycles per step in legacy
 // HMMA issue - mma.sync runs at a fraction of the tcgen05 rate on sm_100.  Here each CTA keeps its W_hh
 // slice [4U gate rows x H] resident in shared memory as the UMMA *B* operand (K-major, 128B swizzle, loaded
-// once by TMA), streams h_{t-1} [batch x H] (fp16, published by all CTAs) through a 4-stage TMA ring as
-// the *A* operand (M = 128 batch rows), and accumulates gates[batch, 4U] in TMEM: 96 tcgen05.mma of
-// 128 x 4U x 16 per step (24 cycles each) instead of 2304 HMMA.  8 epilogue warps read TMEM (lane = batch
-// row), add the precomputed input projection, do the cell update (c in registers) and publish h_t; a
-// flag-per-CTA grid barrier separates the steps.
+// once by TMA) and streams h_{t-1} (fp16, published by all CTAs) through a TMA ring as the *A* operand;
+// gates accumulate in TMEM.
+//
+// The batch is split into GROUPS of 32 rows that are independent recurrences: group g lives in TMEM lane
+// quadrant g (A-tile rows 32g..32g+31, own accumulator columns, own flags, own epilogue warps g and g+4).
+// The groups are software-pipelined: while group g waits for the grid-wide publication of its h_t (epilogue +
+// fence + flag round trip), the TMA/MMA pipeline is busy with the other groups' steps.  An A tile always spans
+// 128 rows; a group's 4 KB K-block sits at tile row 32g by pointing the UMMA descriptor 4g KB below the slot
+// (same 128B-swizzle phase since 32 rows = 4 x 1024 B); the other rows read whatever finite fp16 data
+// neighbours the slot and only produce garbage in D rows nobody reads.
 // W rows are pre-permuted by the host to unit-major order: row (4*j + g) of CTA c = gate g of unit c*U + j.
 #include <atomic>
 #include <cstdio>
@@ -20,21 +25,29 @@
 namespace qb {
 extern std::atomic<long long> g_launches;
 
-constexpr int LT_EPI_WARPS = 8, LT_THREADS = (LT_EPI_WARPS + 2) * 32, LT_MAX_STAGES = 8;
-constexpr int LT_REP = 1;                        // replicas of the published h (readers pick blockIdx % LT_REP)
-constexpr int LT_KG = 4;                         // K-blocks fetched by one TMA instruction (4-D box)
-constexpr uint32_t LT_RING_BYTES = 72 * 1024;   // 8 x 8 KB slots + 8 KB pad (batch 64) or 4 x 16 KB (+ pad)
+constexpr int LT_EPI_WARPS = 8, LT_THREADS = (LT_EPI_WARPS + 2) * 32;
+constexpr int LT_KG = 4;                          // K-blocks fetched by one TMA instruction (5-D box)
+constexpr int LT_STAGES = 4;                      // ring: 4 x (LT_KG x 4 KB) = 64 KB
+constexpr uint32_t LT_KBLK = 32 * 128;            // one K-block of one group: 32 rows x 128 B
+constexpr uint32_t LT_SLOT = LT_KBLK * LT_KG;
+constexpr uint32_t LT_PAD = 12 * 1024;            // A tiles read up to 12 KB past a group-0 K-block
 
 __device__ __forceinline__ unsigned lt_ld_acquire(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, uint64_t* bar, int x, int y, int z, int w) {
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z), "r"(w)
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+// linear bulk copy global -> shared (no tensor map): the published h is stored tile-native (pre-swizzled)
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -46,40 +59,35 @@ template <int U>
 __global__ void __launch_bounds__(LT_THREADS, 1)
 lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
                const float* __restrict__ xp, int B, int T, int H, __half* __restrict__ out_hi,
-               __half* __restrict__ out_lo, __half* hbuf, unsigned* flags, int Bp, int box_rows, long long* prof) {
+               __half* __restrict__ out_lo, __half* hbuf, unsigned* flags, int Bp, int n_groups, long long* prof) {
   constexpr int N = 4 * U;                      // gate rows of this CTA = UMMA N
   constexpr int HALF = U / 2;                   // units per epilogue thread
-  static_assert(N % 16 == 0 && N <= 256 && HALF * 4 % 8 == 0, "unsupported slice width");
+  static_assert(N % 16 == 0 && N <= 64 && HALF * 4 % 8 == 0, "unsupported slice width");
   constexpr uint32_t WBLK = N * 128;            // bytes of one [N x 64] K-block of W
+  constexpr uint32_t TCOLS = 4 * N <= 64 ? 64 : (4 * N <= 128 ? 128 : 256);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int KB = H / 64;
   uint8_t* Wsm = smem;
-  uint8_t* ring = smem + (size_t)KB * WBLK;     // KB*WBLK is a multiple of 1024 when N % 8 == 0
-  // ring slots hold box_rows (64 or 128) rows; the UMMA A tile always spans 128 rows, so with 64-row slots
-  // the upper half of a tile aliases the next slot (finite values -> garbage only in the unused D rows)
-  const uint32_t kblk_bytes = (uint32_t)box_rows * 128;              // one K-block of h in the ring
-  const uint32_t slot_bytes = kblk_bytes * LT_KG;                      // one TMA instruction
-  const int n_stages = (box_rows == 64 ? 8 : 4) / LT_KG;
-  uint64_t* full = (uint64_t*)(ring + LT_RING_BYTES);
-  uint64_t* empty = full + LT_MAX_STAGES;
-  uint64_t* wbar = empty + LT_MAX_STAGES;
-  uint64_t* tfull = wbar + 1;
-  uint32_t* tmem_slot = (uint32_t*)(tfull + 1);
+  uint8_t* ring = smem + (size_t)KB * WBLK;     // KB*WBLK is a multiple of 1024 (N % 8 == 0)
+  uint64_t* full = (uint64_t*)(ring + LT_STAGES * LT_SLOT + LT_PAD);
+  uint64_t* empty = full + LT_STAGES;
+  uint64_t* wbar = empty + LT_STAGES;
+  uint64_t* tfull = wbar + 1;                   // [4] one per group
+  uint32_t* tmem_slot = (uint32_t*)(tfull + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int u0 = blockIdx.x * U, G = gridDim.x;
-  const int passes = (Bp + 127) / 128;
-  constexpr uint32_t TCOLS = 2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : (2 * N <= 256 ? 256 : 512));
 
   if (tid == 0) {
-    for (int s = 0; s < LT_MAX_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < LT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(wbar, 1);
-    mbar_init(tfull, 1);
+    for (int g = 0; g < 4; ++g) mbar_init(&tfull[g], 1);
     fence_mbar_init();
   }
-  // zero the ring once: rows beyond the TMA box (batch < 128) must stay finite
-  for (int i = tid; i < (int)(LT_RING_BYTES / 16); i += LT_THREADS) reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
+  // ring + pad zeroed once: tile rows outside a group's K-block must be finite
+  for (int i = tid; i < (int)((LT_STAGES * LT_SLOT + LT_PAD) / 16); i += LT_THREADS)
+    reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   if (warp == LT_EPI_WARPS + 1) { tmem_alloc(tmem_slot, TCOLS); tmem_relinquish(); }
   tc_fence_before();
@@ -96,143 +104,142 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       for (int kb = 0; kb < KB; ++kb) tma_load_2d(Wsm + (size_t)kb * WBLK, &tmW, wbar, kb * 64, blockIdx.x * N);
     }
     uint32_t stage = 0, phase = 0;
-    long long pw = 0, pl = 0;
+    long long pw = 0;
     for (int t = 1; t < T; ++t) {
-      // wait until every CTA has published h_{t-1}
-      long long c0 = clock64();
-      unsigned spins = 0;
-      for (;;) {
-        bool ok = true;
-        for (int c = lane; c < G; c += 32) ok = ok && (lt_ld_acquire(flags + c) >= (unsigned)t);
-        if (__all_sync(0xffffffffu, ok)) break;
-        if (++spins > (1u << 26)) asm volatile("trap;");
-      }
-      long long c1 = clock64();
-      pw += c1 - c0;
-      if (lane == 0) {
-        asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy writes of h -> async-proxy (TMA) reads
-        const int buf = (t + 1) & 1;                            // h_{t-1} lives in buffer (t-1)&1
-        for (int ps = 0; ps < passes; ++ps)
+      for (int g = 0; g < n_groups; ++g) {
+        // wait until every CTA has published h_{t-1} of group g
+        const long long c0 = clock64();
+        const unsigned* fl = flags + (size_t)g * G;
+        unsigned spins = 0;
+        for (;;) {
+          bool ok = true;
+          for (int c = lane; c < G; c += 32) ok = ok && (lt_ld_acquire(fl + c) >= (unsigned)t);
+          if (__all_sync(0xffffffffu, ok)) break;
+          __nanosleep(64);                                      // back off: 128 CTAs polling the same 4 lines
+          if (++spins > (1u << 24)) asm volatile("trap;");
+        }
+        pw += clock64() - c0;
+        if (lane == 0) {
+          asm volatile("fence.proxy.async;" ::: "memory");    // generic-proxy writes of h -> async-proxy (TMA) reads
+          const int buf = (t + 1) & 1;                          // h_{t-1} lives in buffer (t-1)&1
           for (int kb = 0; kb < KB; kb += LT_KG) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], slot_bytes);
-            tma_load_4d(ring + stage * slot_bytes, &tmH, &full[stage], 0, ps * 128, kb, buf);
-            if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
+            mbar_arrive_expect_tx(&full[stage], LT_SLOT);
+            bulk_load_1d(ring + stage * LT_SLOT, hbuf + (((size_t)buf * n_groups + g) * KB + kb) * (LT_KBLK / 2), LT_SLOT,
+                         &full[stage]);
+            if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
           }
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      pl += clock64() - c1;
     }
-    if (prof && lane == 0 && blockIdx.x == 0) { prof[0] = pw; prof[1] = pl; }
+    if (prof && lane == 0 && blockIdx.x == 0) prof[0] = pw;
   } else if (warp == LT_EPI_WARPS + 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(128, N);
       mbar_wait(wbar, 0);
       uint32_t stage = 0, phase = 0;
-      long long mw = 0, mfirst = 0;
       for (int t = 1; t < T; ++t) {
-        long long m0 = clock64();
-        for (int ps = 0; ps < passes; ++ps) {
-          const uint32_t d_tmem = tmem_base + ps * N;
+        for (int g = 0; g < n_groups; ++g) {
+          const uint32_t d_tmem = tmem_base + g * N;
           for (int kb0 = 0; kb0 < KB; kb0 += LT_KG) {
             mbar_wait(&full[stage], phase);
-            if (ps == 0 && kb0 == 0) { const long long m1 = clock64(); mfirst += m1 - m0; m0 = m1; }
             tc_fence_after();
 #pragma unroll
-            for (int g = 0; g < LT_KG; ++g) {
-              const int kb = kb0 + g;
-              const uint32_t sa = smem_u32(ring + stage * slot_bytes + g * kblk_bytes), sw = smem_u32(Wsm + (size_t)kb * WBLK);
+            for (int j = 0; j < LT_KG; ++j) {
+              const int kb = kb0 + j;
+              // tile base 4g KB below the K-block: the group's 32 rows are tile rows 32g..32g+31
+              const uint32_t sa = smem_u32(ring + stage * LT_SLOT + j * LT_KBLK) - (uint32_t)g * LT_KBLK;
+              const uint32_t sw = smem_u32(Wsm + (size_t)kb * WBLK);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_f16(d_tmem, make_sw128_kmajor_desc(sa + k * 32), make_sw128_kmajor_desc(sw + k * 32), idesc,
                          (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit(&empty[stage]);
-            if (++stage == (uint32_t)n_stages) { stage = 0; phase ^= 1; }
+            if (++stage == LT_STAGES) { stage = 0; phase ^= 1; }
           }
+          umma_commit(&tfull[g]);
         }
-        umma_commit(tfull);
-        mw += clock64() - m0;
       }
-      if (prof && blockIdx.x == 0) { prof[2] = mfirst; prof[3] = mw; }
     }
   } else {
-    // ===================== epilogue: cell update =====================
-    const int q = warp & 3, half = warp >> 2;            // TMEM lane quadrant, unit half
-    float c[2][HALF];
+    // ===================== epilogue: cell update (warps g and g+4 serve group g) =====================
+    const int g = warp & 3, half = warp >> 2;
+    if (g < n_groups) {
+      float c[HALF];
 #pragma unroll
-    for (int ps = 0; ps < 2; ++ps)
+      for (int i = 0; i < HALF; ++i) c[i] = 0.f;
+      const int n = g * 32 + lane;
+      const bool act = n < B;
+      const int u = u0 + half * HALF;
+      long long ew = 0, ec = 0, ep = 0;
+      for (int t = 0; t < T; ++t) {
+        const long long e0 = clock64();
+        // tile-native layout [buf][group][K-block][32 rows][128 B], 16-byte chunks XOR-swizzled by (row & 7)
+        __half* hcur = hbuf + ((size_t)(t & 1) * n_groups + g) * KB * (LT_KBLK / 2);
+        float xg[4][HALF];
 #pragma unroll
-      for (int i = 0; i < HALF; ++i) c[ps][i] = 0.f;
-    long long ew = 0, ec = 0, ep = 0;
-    for (int t = 0; t < T; ++t) {
-      long long e0 = clock64(), e1 = e0;
-      __half* hcur = hbuf + (size_t)(t & 1) * LT_REP * Bp * H;
+        for (int gg = 0; gg < 4; ++gg)
 #pragma unroll
-      for (int ps = 0; ps < 2; ++ps) {
-        if (ps < passes) {
-          const int n = ps * 128 + q * 32 + lane;
-          const bool act = n < B;
-          // input projection for (row n, units u0 + half*HALF .. +HALF), all 4 gates
-          float xg[4][HALF];
+          for (int i = 0; i < HALF; ++i)
+            xg[gg][i] = act ? xp[((long long)n * T + t) * 4 * H + (long long)gg * H + u + i] : 0.f;
+        float acc[HALF * 4];
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
+        for (int i = 0; i < HALF * 4; ++i) acc[i] = 0.f;
+        long long e1 = e0;
+        if (t > 0) {
+          mbar_wait(&tfull[g], (t - 1) & 1);
+          tc_fence_after();
+          e1 = clock64();
+          const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + g * N + half * HALF * 4;
 #pragma unroll
-            for (int i = 0; i < HALF; ++i)
-              xg[g][i] = act ? xp[((long long)n * T + t) * 4 * H + (long long)g * H + u0 + half * HALF + i] : 0.f;
-          float acc[HALF * 4];
+          for (int cc = 0; cc < HALF * 4; cc += 8) {
+            uint32_t r[8];
+            tmem_ld_32x32b_x8(taddr + cc, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < HALF * 4; ++i) acc[i] = 0.f;
-          if (t > 0) {
-            if (ps == 0) { mbar_wait(tfull, (t - 1) & 1); tc_fence_after(); e1 = clock64(); ew += e1 - e0; }
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ps * N + half * HALF * 4;
-#pragma unroll
-            for (int cc = 0; cc < HALF * 4; cc += 8) {
-              uint32_t r[8];
-              tmem_ld_32x32b_x8(taddr + cc, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int e = 0; e < 8; ++e) acc[cc + e] = __uint_as_float(r[e]);
-            }
-          }
-          if (act) {
-            __half hv[HALF], lv[HALF];
-#pragma unroll
-            for (int i = 0; i < HALF; ++i) {
-              const float gi = acc[4 * i] + xg[0][i], gf = acc[4 * i + 1] + xg[1][i];
-              const float gg = acc[4 * i + 2] + xg[2][i], go = acc[4 * i + 3] + xg[3][i];
-              const float ig = sigmoid_acc(gi), fg = sigmoid_acc(gf), cg = tanhf(gg), og = sigmoid_acc(go);
-              const float cn = fg * c[ps][i] + ig * cg;
-              c[ps][i] = cn;
-              split_f16(og * tanhf(cn), hv[i], lv[i]);
-            }
-            // packed stores: HALF halves are contiguous (4-byte aligned: u0 and HALF are even)
-            const int u = u0 + half * HALF;
-            const long long o = ((long long)n * T + t) * H + u;
-#pragma unroll
-            for (int i = 0; i < HALF; i += 2) {
-              const __half2 h2 = __halves2half2(hv[i], hv[i + 1]);
-#pragma unroll
-              for (int rp = 0; rp < LT_REP; ++rp) *reinterpret_cast<__half2*>(hcur + ((size_t)rp * Bp + n) * H + u + i) = h2;
-              *reinterpret_cast<__half2*>(out_hi + o + i) = h2;
-              if (out_lo) *reinterpret_cast<__half2*>(out_lo + o + i) = __halves2half2(lv[i], lv[i + 1]);
-            }
+            for (int e = 0; e < 8; ++e) acc[cc + e] = __uint_as_float(r[e]);
           }
         }
+        if (act) {
+          __half hv[HALF], lv[HALF];
+#pragma unroll
+          for (int i = 0; i < HALF; ++i) {
+            const float gi = acc[4 * i] + xg[0][i], gf = acc[4 * i + 1] + xg[1][i];
+            const float gc = acc[4 * i + 2] + xg[2][i], go = acc[4 * i + 3] + xg[3][i];
+            const float ig = sigmoid_acc(gi), fg = sigmoid_acc(gf), cg = tanhf(gc), og = sigmoid_acc(go);
+            const float cn = fg * c[i] + ig * cg;
+            c[i] = cn;
+            split_f16(og * tanhf(cn), hv[i], lv[i]);
+          }
+          const long long o = ((long long)n * T + t) * H + u;
+#pragma unroll
+          for (int i = 0; i < HALF; i += 2) {   // HALF halves are contiguous and 4-byte aligned (u0, HALF even)
+            const __half2 h2 = __halves2half2(hv[i], hv[i + 1]);
+            {
+              const int uu = u + i, kbk = uu >> 6, col = uu & 63;
+              const int off = kbk * (int)(LT_KBLK / 2) + lane * 64 + ((((col >> 3) ^ (lane & 7)) << 3) | (col & 7));
+              *reinterpret_cast<__half2*>(hcur + off) = h2;
+            }
+            *reinterpret_cast<__half2*>(out_hi + o + i) = h2;
+            if (out_lo) *reinterpret_cast<__half2*>(out_lo + o + i) = __halves2half2(lv[i], lv[i + 1]);
+          }
+        }
+        // publish h_t of this group: both warps of the group done (TMEM reads + h stores) -> flag
+        tc_fence_before();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory");
+        const long long e2 = clock64();
+        if (half == 0 && lane == 0) {
+          __threadfence();
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + (size_t)g * G + blockIdx.x), "r"((unsigned)(t + 1))
+                       : "memory");
+        }
+        ew += e1 - e0; ec += e2 - e1; ep += clock64() - e2;
       }
-      // publish h_t: all epilogue threads done (TMEM reads + h stores) -> flag
-      tc_fence_before();
-      asm volatile("bar.sync 1, %0;" ::"n"(LT_EPI_WARPS * 32) : "memory");
-      const long long e2 = clock64();
-      ec += e2 - e1;
-      if (tid == 0) {
-        __threadfence();
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + blockIdx.x), "r"((unsigned)(t + 1)) : "memory");
-        ep += clock64() - e2;
-      }
+      if (prof && warp == 0 && lane == 0 && blockIdx.x == 0) { prof[4] = ew; prof[5] = ec; prof[6] = ep; }
     }
-    if (prof && tid == 0 && blockIdx.x == 0) { prof[4] = ew; prof[5] = ec; prof[6] = ep; }
   }
   tc_fence_before();
   __syncthreads();
@@ -258,6 +265,57 @@ static EncodeTiledFn lt_encode() {
   return fn;
 }
 
+static int lstm_tc_chunk(const float* xp, const qb_half* whh_perm, int U, int B, int64_t T, int64_t H, __half* oh, __half* ol,
+                         void* workspace, cudaStream_t st) {
+  const int N = 4 * U, grid = (int)(H / U), KB = (int)(H / 64);
+  const int n_groups = (B + 31) / 32, Bp = n_groups * 32;
+  EncodeTiledFn enc = lt_encode();
+  QB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available");
+  CUtensorMap tmW, tmH;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)(4 * H)};
+    cuuint64_t str[1] = {(cuuint64_t)H * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)N};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)whh_perm, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    QB_REQUIRE(r == CUDA_SUCCESS, "lstm_tc: W tensor map failed (%d)", (int)r);
+  }
+  __half* hbuf = (__half*)workspace;
+  {
+    // 5-D view (k within block, row within group, K-block, buffer, group): one box = LT_KG K-block tiles of a group
+    cuuint64_t dims[5] = {64, 32, (cuuint64_t)(H / 64), 2, (cuuint64_t)n_groups};
+    cuuint64_t str[4] = {(cuuint64_t)H * 2, 128, (cuuint64_t)Bp * H * 2, (cuuint64_t)32 * H * 2};
+    cuuint32_t box[5] = {64, 32, LT_KG, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tmH, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)hbuf, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    QB_REQUIRE(r == CUDA_SUCCESS, "lstm_tc: h tensor map failed (%d)", (int)r);
+  }
+  const size_t smem = (size_t)KB * N * 128 + (size_t)LT_STAGES * LT_SLOT + LT_PAD + 1024 + 256;
+  QB_REQUIRE(smem <= 227 * 1024, "lstm_tc: shared memory budget exceeded (%zu)", smem);
+  const size_t hbytes = (size_t)2 * Bp * H * 2;
+  QB_CHECK_CUDA(cudaMemsetAsync(workspace, 0, hbytes + 4096, st));
+  unsigned* flags = (unsigned*)((uint8_t*)workspace + hbytes);
+  static long long* prof = nullptr;
+  if (!prof && getenv("QB_LSTM_PROF")) { cudaMalloc(&prof, 64); cudaMemset(prof, 0, 64); }
+  int Bi = B, Ti = (int)T, Hi = (int)H, Bpi = Bp, ng = n_groups;
+  void* args[] = {&tmW, &tmH, &xp, &Bi, &Ti, &Hi, &oh, &ol, &hbuf, &flags, &Bpi, &ng, &prof};
+  const void* fn = U == 4 ? (const void*)lstm_tc_kernel<4> : U == 8 ? (const void*)lstm_tc_kernel<8> : (const void*)lstm_tc_kernel<12>;
+  QB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  QB_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LT_THREADS), args, smem, st));
+  g_launches++;
+  if (prof) {
+    long long h[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, prof, 64, cudaMemcpyDeviceToHost);
+    const double d = (double)Ti;
+    fprintf(stderr, "[lstm_tc prof] cycles/step (cta0): producer flag-wait %.0f | epilogue(group0) wait-acc %.0f compute %.0f publish %.0f\n",
+            h[0] / d, h[4] / d, h[5] / d, h[6] / d);
+  }
+  return 0;
+}
+
 }  // namespace qb
 using namespace qb;
 
@@ -271,8 +329,9 @@ extern "C" int32_t qb_lstm_tc_units(int64_t H) {
 }
 
 extern "C" int64_t qb_lstm_tc_workspace_bytes(int64_t B, int64_t H) {
-  const int64_t Bp = B <= 64 ? 64 : ceil_div(B, 128) * 128;
-  return 2 * LT_REP * Bp * H * 2 + 4096;
+  const int64_t Bc = B < 128 ? B : 128;                 // rows processed by one launch
+  const int64_t Bp = ceil_div(Bc, 32) * 32;
+  return 2 * Bp * H * 2 + 4096;
 }
 
 extern "C" int qb_lstm_tc(const float* xp, const qb_half* whh_perm, int32_t units, int64_t B, int64_t T, int64_t H,
@@ -280,55 +339,12 @@ extern "C" int qb_lstm_tc(const float* xp, const qb_half* whh_perm, int32_t unit
   cudaStream_t st = (cudaStream_t)stream;
   QB_REQUIRE(xp && whh_perm && out_hi && workspace, "lstm_tc: bad args");
   QB_REQUIRE(H % (64 * LT_KG) == 0 && (units == 4 || units == 8 || units == 12) && H % units == 0, "lstm_tc: unsupported H / units");
-  QB_REQUIRE(B >= 1 && B <= 256, "lstm_tc: batch must be 1..256 per call (got %lld)", (long long)B);
-  const int U = units, N = 4 * U, grid = (int)(H / U), KB = (int)(H / 64);
-  const int Bp = (int)(B <= 64 ? 64 : ceil_div(B, 128) * 128);
-  const int box_rows = Bp < 128 ? Bp : 128;
-  EncodeTiledFn enc = lt_encode();
-  QB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available");
-  CUtensorMap tmW, tmH;
-  cuuint32_t es[3] = {1, 1, 1};
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)(4 * H)};
-    cuuint64_t str[1] = {(cuuint64_t)H * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)N};
-    CUresult r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)whh_perm, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    QB_REQUIRE(r == CUDA_SUCCESS, "lstm_tc: W tensor map failed (%d)", (int)r);
-  }
-  __half* hbuf = (__half*)workspace;
-  {
-    // 4-D view (k within block, batch row, K-block, buffer): one box = LT_KG consecutive K-block tiles
-    cuuint64_t dims[4] = {64, (cuuint64_t)Bp, (cuuint64_t)(H / 64), 2};
-    cuuint64_t str[3] = {(cuuint64_t)H * 2, 128, (cuuint64_t)Bp * H * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)box_rows, LT_KG, 1};
-    cuuint32_t es4[4] = {1, 1, 1, 1};
-    (void)es;
-    CUresult r = enc(&tmH, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)hbuf, dims, str, box, es4, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    QB_REQUIRE(r == CUDA_SUCCESS, "lstm_tc: h tensor map failed (%d)", (int)r);
-  }
-  const size_t smem = (size_t)KB * N * 128 + (size_t)LT_RING_BYTES + 1024 + 256;
-  QB_REQUIRE(smem <= 227 * 1024, "lstm_tc: shared memory budget exceeded (%zu)", smem);
-  QB_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)qb_lstm_tc_workspace_bytes(B, H), st));
-  unsigned* flags = (unsigned*)((uint8_t*)workspace + (size_t)2 * LT_REP * Bp * H * 2);
-  __half* oh = (__half*)out_hi;
-  __half* ol = (__half*)out_lo;
-  int Bi = (int)B, Ti = (int)T, Hi = (int)H, Bpi = Bp, br = box_rows;
-  static long long* prof = nullptr;
-  if (!prof && getenv("QB_LSTM_PROF")) { cudaMalloc(&prof, 64); cudaMemset(prof, 0, 64); }
-  void* args[] = {&tmW, &tmH, &xp, &Bi, &Ti, &Hi, &oh, &ol, &hbuf, &flags, &Bpi, &br, &prof};
-  const void* fn = U == 4 ? (const void*)lstm_tc_kernel<4> : U == 8 ? (const void*)lstm_tc_kernel<8> : (const void*)lstm_tc_kernel<12>;
-  QB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  QB_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LT_THREADS), args, smem, st));
-  g_launches++;
-  if (prof) {
-    long long h[8];
-    cudaStreamSynchronize(st);
-    cudaMemcpy(h, prof, 64, cudaMemcpyDeviceToHost);
-    const double d = (double)Ti;
-    fprintf(stderr, "[lstm_tc prof] cycles/step: producer flag-wait %.0f tma-issue %.0f | mma first-block wait %.0f rest %.0f | "
-            "epilogue wait-acc %.0f compute %.0f publish %.0f\n", h[0] / d, h[1] / d, h[2] / d, h[3] / d, h[4] / d, h[5] / d, h[6] / d);
+  QB_REQUIRE(B >= 1, "lstm_tc: empty batch");
+  for (int64_t b0 = 0; b0 < B; b0 += 128) {              // <= 4 groups of 32 rows per launch
+    const int bc = (int)(B - b0 < 128 ? B - b0 : 128);
+    if (int e = lstm_tc_chunk(xp + b0 * T * 4 * H, whh_perm, units, bc, T, H, (__half*)out_hi + b0 * T * H,
+                              out_lo ? (__half*)out_lo + b0 * T * H : nullptr, workspace, st))
+      return e;
   }
   return 0;
 }
