@@ -127,3 +127,51 @@ def test_h2_full_config_vs_oracle(lib):
     ref = hcodec2.codec_decode(sd, cfg, oa, os_)
     print(f"[full/mixed] wav rel {rel(rec, ref):.2e} l2 {l2(rec, ref):.2e}")
     assert rel(rec, ref) < TOL
+
+
+def test_h2_ragged_sizes_vs_oracle(lib):
+    """odd batch / token counts (partial M tiles, LSTM groups with < 32 rows, CTA-pair fallbacks)"""
+    from oracle import hcodec2, weights
+    cfg = weights.h2_small()
+    model, sd = build(cfg, 5, "mixed")
+    for B, ntok in ((1, 1), (3, 5), (33, 2)):
+        wav, feat = weights.synth_inputs(cfg, B, ntok, 77 + B)
+        oa, os_ = hcodec2.codec_encode(sd, cfg, wav, feat)
+        emb = hcodec2.encoder_forward(sd, cfg["encoder_config"], wav)
+        taps = {}
+        ac, sc = model.encode(wav.cuda(), feat.cuda(), taps=taps)
+        rec = model.decode(oa.cuda(), os_.cuda())
+        torch.cuda.synchronize()
+        ref = hcodec2.codec_decode(sd, cfg, oa, os_)
+        print(f"[ragged B={B} N={ntok}] emb rel {rel(taps['enc.out'], emb):.2e} wav rel {rel(rec, ref):.2e} "
+              f"code match {float((ac.cpu() == oa).float().mean()):.4f}")
+        assert rel(taps["enc.out"], emb) < TOL and rel(rec, ref) < TOL and rec.shape == (B, ntok * 3840)
+        with pytest.raises(ValueError):
+            model.encode(wav[:, :-1].cuda(), feat.cuda())          # length not a multiple of 3840 (pad_wav contract)
+
+
+def test_h2_full_size_properties(lib):
+    """BASELINE-size clips (10 s @ 48 kHz, shipped config): size-independent properties instead of a CPU oracle run -
+    run-to-run determinism, batch invariance (clip i of a batch == the same clip alone), output length."""
+    from oracle import weights
+    cfg = weights.H2_FULL
+    model, _ = build(cfg, 0, "mixed")
+    B, ntok = 6, 125
+    wav, feat = weights.synth_inputs(cfg, B, ntok, 4242)
+    wav, feat = wav.cuda(), feat.cuda()
+    ac1, sc1 = model.encode(wav, feat)
+    rec1 = model.decode(ac1, sc1).clone()
+    ac2, sc2 = model.encode(wav, feat)
+    rec2 = model.decode(ac2, sc2)
+    torch.cuda.synchronize()
+    assert torch.equal(ac1, ac2) and torch.equal(sc1, sc2) and torch.equal(rec1, rec2), "non-deterministic"
+    assert ac1.shape == (B, 16, ntok) and rec1.shape == (B, ntok * 3840) and bool(torch.isfinite(rec1).all())
+    i = 4
+    aci, sci = model.encode(wav[i:i + 1].contiguous(), feat[i:i + 1].contiguous())
+    reci = model.decode(ac1[i:i + 1].contiguous(), sc1[i:i + 1].contiguous())
+    torch.cuda.synchronize()
+    match = float((aci == ac1[i:i + 1]).float().mean())
+    e = rel(reci, rec1[i:i + 1])
+    print(f"[full-size] batch invariance: code match {match:.4f}, wav rel {e:.2e}")
+    assert match == 1.0 and e < 1e-5
+    assert int(ac1.min()) >= 0 and int(ac1.max()) < 1024
