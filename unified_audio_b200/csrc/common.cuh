@@ -186,7 +186,7 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load executed by both CTAs of a pair; completion bytes are signalled on `bar_cluster_addr` (the leader's barrier)
 __device__ __forceinline__ void tma2_load_2d(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr, int x, int y) {

@@ -91,6 +91,51 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int b, int m
         if (n_base + j < p.N) v[j] += __ldg(p.bias + n_base + j);
     }
   }
+  // ---- specialised tight paths (no per-element predicates) for the two epilogues that carry >90 % of the
+  //      single-pass GEMM work: ConvNeXt pwconv1 (bias + GELU -> fp16 hi plane) and pwconv2 (bias, gamma,
+  //      + residual -> fp32).  Everything else takes the generic path below.
+  if (n_base + 32 <= p.N && p.act2 == QB_ACT_NONE && (p.act == QB_ACT_NONE || p.act == QB_ACT_GELU)) {
+    if (p.ohi.ptr && !p.olo.ptr && !p.o32.ptr && !p.res.ptr && !p.gamma && (p.ohi.ld & 7) == 0) {
+      if (p.act == QB_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+      }
+      uint4* hp = (uint4*)((__half*)p.ohi.ptr + ((long long)b * p.ohi.rpb + p.ohi.off + m) * p.ohi.ld + n_base);
+      const __half2 hmax = __float2half2_rn(65504.f), hmin = __float2half2_rn(-65504.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __half2 h2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          h2[e] = __hmax2(__hmin2(__floats2half2_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]), hmax), hmin);
+        hp[j] = *reinterpret_cast<uint4*>(h2);
+      }
+      return;
+    }
+    if (p.o32.ptr && !p.ohi.ptr && (p.o32.ld & 3) == 0 && (!p.res.ptr || (p.res.ld & 3) == 0) && p.act == QB_ACT_NONE &&
+        (!p.gamma || (reinterpret_cast<uintptr_t>(p.gamma) & 15) == 0)) {
+      if (p.gamma) {
+        const float4* gp = reinterpret_cast<const float4*>(p.gamma + n_base);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = __ldg(gp + j);
+          v[4 * j] *= t.x; v[4 * j + 1] *= t.y; v[4 * j + 2] *= t.z; v[4 * j + 3] *= t.w;
+        }
+      }
+      if (p.res.ptr) {
+        const float4* rp = (const float4*)((const float*)p.res.ptr + ((long long)b * p.res.rpb + p.res.off + m) * p.res.ld + n_base);
+        float4 t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = rp[j];          // all 8 loads in flight before the adds
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[4 * j] += t[j].x; v[4 * j + 1] += t[j].y; v[4 * j + 2] += t[j].z; v[4 * j + 3] += t[j].w; }
+      }
+      float4* op = (float4*)((float*)p.o32.ptr + ((long long)b * p.o32.rpb + p.o32.off + m) * p.o32.ld + n_base);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      return;
+    }
+  }
   int ncols = 32, n_out = n_base, N_out = p.N;
   if (p.act == QB_ACT_SWIGLU) {
 #pragma unroll
