@@ -265,14 +265,14 @@ def run_lm(args):
     gbs = total_bytes / (ms * 1e-3) / 1e9
     print(json.dumps(dict(metric="unise_sr_arlm_generate_tokens_per_s", value=B * 283 / (ms * 1e-3), unit="tokens/s", n_gpus=1,
                           steps=args.steps, warmup=max(args.warmup, 1), ms_per_step=ms, higher_is_better=True, scaling="weak",
-                          vs_baseline=None, dtype="f32 decode / f16x3 prefill", data="synthetic",
+                          vs_baseline=None, dtype="f16x3 split tensor-core (fp32-grade), f32 accumulate / f32 KV cache", data="synthetic",
                           config=dict(workload="UniSE SR AR-LM greedy generate (prefill 252 + 33 + 250 cached steps), batch=32",
                                       batch=B, semantic_length=T),
                           e2e=dict(value=B * 283 / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=int(mix_h.numel() * 4),
                                    d2h_bytes_per_step=B * 282 * 8),
                           gpu_launches=int(launches),
                           roofline=dict(bound="hbm", achieved=gbs, peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"],
-                                        traffic=None, kernel="decode step (lm_gemv + lm_decode_attn), algorithmic bytes = fp32 "
+                                        traffic=None, kernel="decode step (lm_skinny<QKV|RESID|GATEUP|HEAD> + lm_decode_attn2), algorithmic bytes = 4 B/param packed "
                                         "weights + head slice + fp32 KV read per step, whole generate incl. prefill"))))
 
 

@@ -224,6 +224,26 @@ int qb_lm_head_argmax(const float* x, int64_t B, int32_t hidden, const float* fi
                       int64_t* out_ids, int32_t out_stride, int32_t* pos, int32_t* slot, float* part_val,
                       int32_t* part_idx, void* stream);
 
+/* ---- tensor-core decode step (the product path; the fp32 kernels above stay as the cross-check) ----
+ * Weights are pre-packed ONCE with qb_lm_pack_weight: row-major [n][k] fp32 -> [n][k/4] 16-byte groups
+ * {hi[4], lo[4]} of fp16 (hi = rn16(w), lo = rn16(w - hi)): 4 bytes / parameter like fp32, and one 16-byte load is
+ * directly the B fragment of two MMA k-slots.  Same folding contract as qb_lm_decode_layer (RMSNorm weights folded
+ * into wqkv / wgate / wup / w_head BEFORE packing).  Each kernel issues its weight loads before
+ * `griddepcontrol.wait` and is launched as a programmatic dependent of its predecessor (works inside stream capture;
+ * QB_LM_PDL=0 disables), products are 3-term fp16-split mma.sync tiles with fp32 accumulation.
+ * Replaces: HF Llama decoder layer on one cached token - QuarkAudio-UniSE/model/llm/llm.py:195-228 driven by
+ * llm_sft.py:155-191. */
+int qb_lm_pack_weight(const float* w, int64_t n, int64_t k, qb_half* out /* [n][2k] */, void* stream);
+int qb_lm_decode_layer_tc(float* x, int64_t B, int32_t hidden, int32_t heads, int32_t inter, const qb_half* wqkv,
+                          const qb_half* wo, const qb_half* wgate, const qb_half* wup, const qb_half* wdown,
+                          float* k_cache, float* v_cache, int32_t Lmax, const int32_t* pos, const float* rope_cos,
+                          const float* rope_sin, float* q_buf, float* attn_buf, float* mlp_buf, void* stream);
+/* as qb_lm_head_argmax with a packed head; max_cols and the range width must be multiples of 16;
+ * part_val/part_idx: scratch [max_cols/16 * 32]. */
+int qb_lm_head_argmax_tc(const float* x, int64_t B, int32_t hidden, const qb_half* w_head, const int32_t* range,
+                         int32_t max_cols, const float* embedding, float* x_next, int64_t* out_ids, int32_t out_stride,
+                         int32_t* pos, int32_t* slot, float* part_val, int32_t* part_idx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

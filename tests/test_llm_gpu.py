@@ -97,3 +97,28 @@ def test_lm_full_config_vs_oracle(lib):
     zero = torch.zeros(B, 1, dtype=torch.long)
     compare_tokens("full generate", torch.cat([gg.cpu(), zero, ss.cpu()], 1), torch.cat([og, zero, os_], 1), margins)
     print("min oracle margin", float(margins.min()))
+
+
+@pytest.mark.parametrize("B", [1, 5, 32])
+def test_lm_decode_kernels_agree(lib, B):
+    """The product decode step (packed fp16-split weights, mma.sync, programmatic dependent launch) against the
+    fp32 SIMT kernels and the oracle: cached single-token hidden states after a 40-token prefill."""
+    from oracle import llama
+    cfg = llama.LM_FULL
+    m, sd = build(cfg, 3, 2.0)
+    g = torch.Generator().manual_seed(100 + B)
+    x = torch.randn(B, 46, 512, generator=g)
+    ref, _ = llama.llm_forward(sd, cfg, x)
+    outs = {}
+    for kern in ("tc", "simt"):
+        m.decode_kernel = kern
+        out = m.llm_forward(x[:, :40].cuda(), use_cache=True)
+        cache = out.past_key_values
+        hs = []
+        for i in range(40, 46):
+            hs.append(m.llm_forward(x[:, i:i + 1].cuda(), past_key_values=cache, use_cache=True).last_hidden_state)
+        torch.cuda.synchronize()
+        outs[kern] = torch.cat(hs, 1)
+    e_tc, e_simt, e_x = rel(outs["tc"], ref[:, 40:]), rel(outs["simt"], ref[:, 40:]), rel(outs["tc"], outs["simt"])
+    print(f"B={B}: decode rel vs oracle tc {e_tc:.2e} simt {e_simt:.2e}; tc vs simt {e_x:.2e}")
+    assert e_tc < TOL and e_simt < TOL and e_x < 1e-4

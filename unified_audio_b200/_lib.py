@@ -69,6 +69,10 @@ SIGNATURES = {
     "qb_lm_decode_layer": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp,
                                       _vp, _vp, _vp, _vp, _vp, _vp]),
     "qb_lm_head_argmax": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "qb_lm_pack_weight": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
+    "qb_lm_decode_layer_tc": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
+                                        _vp, _vp, _vp, _vp]),
+    "qb_lm_head_argmax_tc": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -497,6 +497,8 @@ __global__ void lm_argmax_embed_kernel(const float* __restrict__ part_val, const
                                        int B, const float* __restrict__ emb, int Hd, float* __restrict__ x_next,
                                        int64_t* __restrict__ out_ids, int out_stride, int* __restrict__ pos,
                                        int* __restrict__ slot) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");          // no-ops unless launched as a programmatic dependent
   const int b = blockIdx.x;
   __shared__ float sv[32];
   __shared__ int si[32];
@@ -530,6 +532,294 @@ __global__ void lm_argmax_embed_kernel(const float* __restrict__ part_val, const
     __threadfence();
     const int done = atomicAdd(slot + 1, 1);          // slot[1] = arrival counter
     if (done == B - 1) { slot[1] = 0; *slot += 1; *pos += 1; }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------ decode step, tensor-core path
+// The fp32 SIMT kernels above spend their time in shared-memory reads (every warp re-reads the whole x tile for
+// one or two output columns) and in 32-way shuffle reductions.  The product path below keeps the same fusion
+// (RMSNorm folded into W, RoPE + cache append / residual / SwiGLU / arg-max partials in the epilogue) but runs
+// the [32 x K] . [K x 8] products as 3-term fp16-split mma.sync tiles:
+//   * weights are pre-packed once (qb_lm_pack_weight) as uint4 {hi[4], lo[4]} per 4 consecutive k of a row:
+//     the same 4 bytes / parameter as fp32, zero conversion work on the streaming side, one 16-byte load per lane
+//     that is directly the B fragment of two MMA k-slots (k-slot order inside an MMA is free as long as A agrees);
+//   * each warp owns a contiguous K slice and issues ALL of its weight loads before `griddepcontrol.wait`, so under
+//     programmatic dependent launch the HBM latency of step n+1's weights overlaps the tail of kernel n;
+//   * x is read straight from global/L2 into A fragments (no shared-memory staging), split hi/lo in registers;
+//   * partial tiles of the warps are summed through shared memory in a fixed order (deterministic).
+enum { SK_QKV = 0, SK_RESID = 1, SK_GATEUP = 2, SK_HEAD = 3 };
+
+struct SkParams {
+  const float* x;        // [B,K]
+  int B, K;
+  const uint4* W;        // packed rows [N][K/4]
+  const uint4* W2;       // GATEUP: up-proj rows
+  float eps;
+  float* out;            // RESID: x [B,N] updated in place; GATEUP: [B,N]; QKV: q [B,H*64]
+  int N;
+  int H, Lmax;
+  const int* pos;
+  const float* rcos;
+  const float* rsin;
+  float* kc;
+  float* vc;
+  const int* range;
+  float* part_val;
+  int* part_idx;
+};
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+__global__ void lm_pack_weight_kernel(const float* __restrict__ w, long long total4, uint4* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const float4 v = reinterpret_cast<const float4*>(w)[i];
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(v.x - b0.x, v.y - b0.y), l1 = __floats2half2_rn(v.z - b1.x, v.w - b1.y);
+  uint4 o;
+  o.x = *reinterpret_cast<const uint32_t*>(&h0); o.y = *reinterpret_cast<const uint32_t*>(&h1);
+  o.z = *reinterpret_cast<const uint32_t*>(&l0); o.w = *reinterpret_cast<const uint32_t*>(&l1);
+  out[i] = o;
+}
+
+template <int MODE, int SPW, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+lm_skinny_kernel(const SkParams p) {
+  constexpr int NT = MODE == SK_RESID ? 1 : 2;       // 8-column tiles per CTA
+  __shared__ __align__(16) float red[NW][NT][32][8];
+  __shared__ float ssq[NW][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int K = p.K, K4 = K >> 2, steps_total = K >> 4;
+  // ---- which weight rows
+  const uint4* wrow[NT];
+  bool cta_active = true;
+  int row0 = 0, dd0 = 0, hh = 0, sec = 0;
+  if (MODE == SK_QKV) {
+    dd0 = (blockIdx.x & 3) * 8; hh = (blockIdx.x >> 2) % p.H; sec = blockIdx.x / (4 * p.H);
+    row0 = sec * p.H * 64 + hh * 64 + dd0;
+    wrow[0] = p.W + (size_t)(row0 + g) * K4;
+    if (NT > 1) wrow[NT - 1] = p.W + (size_t)(row0 + 32 + g) * K4;
+  } else if (MODE == SK_RESID) {
+    row0 = blockIdx.x * 8;
+    wrow[0] = p.W + (size_t)(row0 + g) * K4;
+  } else if (MODE == SK_GATEUP) {
+    row0 = blockIdx.x * 8;
+    wrow[0] = p.W + (size_t)(row0 + g) * K4;
+    if (NT > 1) wrow[NT - 1] = p.W2 + (size_t)(row0 + g) * K4;
+  } else {
+    const int lo = p.range[0], ncol = p.range[1] - lo;      // host-written before the graph launch, not by a kernel
+    cta_active = (int)blockIdx.x * 16 < ncol;
+    row0 = lo + (cta_active ? blockIdx.x * 16 : 0);
+    wrow[0] = p.W + (size_t)(row0 + g) * K4;
+    if (NT > 1) wrow[NT - 1] = p.W + (size_t)(row0 + 8 + g) * K4;
+  }
+  // ---- all of this warp's weight fragments in flight before the dependency wait
+  uint4 wv[NT][SPW];
+#pragma unroll
+  for (int s = 0; s < SPW; ++s) {
+    const int step = warp * SPW + s;
+    const bool ok = step < steps_total && cta_active;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) wv[nt][s] = ok ? __ldg(wrow[nt] + step * 4 + t) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  pdl_launch_dependents();
+  pdl_wait();
+  float acc[2][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+  float ss[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int s0 = 0; s0 < SPW; s0 += 4) {       // 4 k-steps of x (16 float4 per lane) in flight at a time
+    float4 xv[4][4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int step = warp * SPW + s0 + s;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int row = r * 8 + g;
+        xv[s][r] = (step < steps_total && row < p.B && cta_active)
+                       ? *reinterpret_cast<const float4*>(p.x + (size_t)row * K + step * 16 + 4 * t)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      uint32_t ah[4][2], al[4][2];      // [row group r][k pair]
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float4 v = xv[s][r];
+        if (MODE != SK_RESID) ss[r] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss[r]))));
+        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        const float2 b0 = __half22float2(h0), b1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(v.x - b0.x, v.y - b0.y), l1 = __floats2half2_rn(v.z - b1.x, v.w - b1.y);
+        ah[r][0] = *reinterpret_cast<const uint32_t*>(&h0); ah[r][1] = *reinterpret_cast<const uint32_t*>(&h1);
+        al[r][0] = *reinterpret_cast<const uint32_t*>(&l0); al[r][1] = *reinterpret_cast<const uint32_t*>(&l1);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const uint4 w = wv[nt][s0 + s];
+          // A regs: {row g k-lo pair, row g+8 k-lo pair, row g k-hi pair, row g+8 k-hi pair}; small terms first
+          l_mma(acc[mt][nt], al[2 * mt][0], al[2 * mt + 1][0], al[2 * mt][1], al[2 * mt + 1][1], w.x, w.y);
+          l_mma(acc[mt][nt], ah[2 * mt][0], ah[2 * mt + 1][0], ah[2 * mt][1], ah[2 * mt + 1][1], w.z, w.w);
+          l_mma(acc[mt][nt], ah[2 * mt][0], ah[2 * mt + 1][0], ah[2 * mt][1], ah[2 * mt + 1][1], w.x, w.y);
+        }
+    }
+  }
+  // ---- cross-warp reduction (fixed order)
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      *reinterpret_cast<float2*>(&red[warp][nt][mt * 16 + g][2 * t]) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+      *reinterpret_cast<float2*>(&red[warp][nt][mt * 16 + g + 8][2 * t]) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+    }
+  if (MODE != SK_RESID) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float q = ss[r];
+      q += __shfl_xor_sync(0xffffffffu, q, 1);
+      q += __shfl_xor_sync(0xffffffffu, q, 2);
+      if (t == 0) ssq[warp][r * 8 + g] = q;
+    }
+  }
+  __syncthreads();
+  if (tid >= 256) return;
+  const int b = tid >> 3, c = tid & 7;
+  float v0 = 0.f, v1 = 0.f, q = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    v0 += red[w][0][b][c];
+    if (NT > 1) v1 += red[w][NT - 1][b][c];
+    if (MODE != SK_RESID) q += ssq[w][b];
+  }
+  if (MODE != SK_RESID) {
+    const float rs = rsqrtf(q / K + p.eps);
+    v0 *= rs;
+    v1 *= rs;
+  }
+  if (MODE == SK_HEAD) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    if (cta_active && b < p.B) {
+      bv = v0; bi = row0 + c;
+      if (v1 > bv) { bv = v1; bi = row0 + 8 + c; }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (c == 0) {
+      p.part_val[(size_t)blockIdx.x * 32 + b] = bv;
+      p.part_idx[(size_t)blockIdx.x * 32 + b] = bi;
+    }
+    return;
+  }
+  if (b >= p.B) return;
+  if (MODE == SK_RESID) {
+    p.out[(size_t)b * p.N + row0 + c] += v0;
+  } else if (MODE == SK_GATEUP) {
+    p.out[(size_t)b * p.N + row0 + c] = silu_f(v0) * v1;
+  } else {  // SK_QKV
+    const int pos = *p.pos, dd = dd0 + c;
+    if (sec < 2) {
+      const float c1 = p.rcos[pos * 64 + dd], s1 = p.rsin[pos * 64 + dd];
+      const float c2 = p.rcos[pos * 64 + dd + 32], s2 = p.rsin[pos * 64 + dd + 32];
+      const float y0 = v0 * c1 - v1 * s1, y1 = v1 * c2 + v0 * s2;
+      if (sec == 0) {
+        p.out[(size_t)b * p.H * 64 + hh * 64 + dd] = y0 * 0.125f;
+        p.out[(size_t)b * p.H * 64 + hh * 64 + dd + 32] = y1 * 0.125f;
+      } else {
+        const size_t o = (((size_t)b * p.H + hh) * p.Lmax + pos) * 64 + dd;
+        p.kc[o] = y0;
+        p.kc[o + 32] = y1;
+      }
+    } else {
+      const size_t o = (((size_t)b * p.H + hh) * p.Lmax + pos) * 64 + dd;
+      p.vc[o] = v0;
+      p.vc[o + 32] = v1;
+    }
+  }
+}
+
+// one CTA per (head, batch row), 16 half-warps each walking keys hw, hw+16, ... with an online softmax; a key row
+// (64 fp32) is one coalesced 256-byte read by 16 lanes, K and V of 4 keys in flight per lane; the 16 partial
+// (max, sum, acc) triples are merged through shared memory in a fixed order.  No score buffer: any cache length.
+__global__ void __launch_bounds__(256)
+lm_decode_attn2_kernel(const float* __restrict__ q, const float* __restrict__ kc, const float* __restrict__ vc, int H,
+                       int Lmax, const int* __restrict__ posp, float* __restrict__ out) {
+  __shared__ __align__(16) float sacc[16][64];
+  __shared__ float sm[16], sl[16];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = lane & 15, hw = warp * 2 + (lane >> 4);
+  const int n = *posp + 1;
+  const float4 qv = *reinterpret_cast<const float4*>(q + (size_t)b * H * 64 + h * 64 + 4 * c);
+  const float4* kb = reinterpret_cast<const float4*>(kc + ((size_t)b * H + h) * Lmax * 64) + c;
+  const float4* vb = reinterpret_cast<const float4*>(vc + ((size_t)b * H + h) * Lmax * 64) + c;
+  float m = -INFINITY, l = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int base = warp * 2; base < n; base += 64) {       // warp-uniform trip count (full-mask shuffles inside)
+    const int j0 = base + (lane >> 4);
+    float4 kv[4], vv[4];
+    float s[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 16 * u;
+      const bool ok = j < n;
+      kv[u] = ok ? kb[(size_t)j * 16] : make_float4(0.f, 0.f, 0.f, 0.f);
+      vv[u] = ok ? vb[(size_t)j * 16] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float d = fmaf(qv.x, kv[u].x, fmaf(qv.y, kv[u].y, fmaf(qv.z, kv[u].z, qv.w * kv[u].w)));
+      d += __shfl_xor_sync(0xffffffffu, d, 8);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      s[u] = (j0 + 16 * u < n) ? d : -INFINITY;
+    }
+    const float mn = fmaxf(fmaxf(m, fmaxf(s[0], s[1])), fmaxf(s[2], s[3]));
+    if (mn > -INFINITY) {                       // (the odd half-warp can run out of keys one trip early)
+      const float corr = expf(m - mn);
+      l *= corr;
+      acc.x *= corr; acc.y *= corr; acc.z *= corr; acc.w *= corr;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float pr = expf(s[u] - mn);
+        l += pr;
+        acc.x = fmaf(pr, vv[u].x, acc.x); acc.y = fmaf(pr, vv[u].y, acc.y);
+        acc.z = fmaf(pr, vv[u].z, acc.z); acc.w = fmaf(pr, vv[u].w, acc.w);
+      }
+      m = mn;
+    }
+  }
+  *reinterpret_cast<float4*>(&sacc[hw][4 * c]) = acc;
+  if (c == 0) { sm[hw] = m; sl[hw] = l; }
+  __syncthreads();
+  if (tid < 64) {
+    float M = sm[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) M = fmaxf(M, sm[i]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float e = expf(sm[i] - M);
+      num = fmaf(e, sacc[i][tid], num);
+      den = fmaf(e, sl[i], den);
+    }
+    out[(size_t)b * H * 64 + h * 64 + tid] = num / den;
   }
 }
 
@@ -635,5 +925,91 @@ extern "C" int qb_lm_head_argmax(const float* x, int64_t B, int32_t hidden, cons
                                                      out_ids, out_stride, pos, slot);
   g_launches++;
   QB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ tensor-core decode (product path)
+static bool lm_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("QB_LM_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = lm_pdl_enabled() ? 1 : 0;
+  g_launches++;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+template <int MODE>
+static int launch_skinny(const SkParams& p, int n_ctas, cudaStream_t st) {
+  QB_REQUIRE(p.K % 16 == 0 && p.K <= 2048, "lm decode: K = %d unsupported (multiple of 16, <= 2048)", p.K);
+  cudaError_t e;
+  if (p.K <= 512) e = launch_pdl(lm_skinny_kernel<MODE, 4, 8>, dim3((unsigned)n_ctas), dim3(256), 0, st, p);
+  else if (p.K <= 1024) e = launch_pdl(lm_skinny_kernel<MODE, 4, 16>, dim3((unsigned)n_ctas), dim3(512), 0, st, p);
+  else e = launch_pdl(lm_skinny_kernel<MODE, 8, 16>, dim3((unsigned)n_ctas), dim3(512), 0, st, p);
+  QB_CHECK_CUDA(e);
+  return 0;
+}
+
+extern "C" int qb_lm_pack_weight(const float* w, int64_t n, int64_t k, qb_half* out, void* stream) {
+  QB_REQUIRE(w && out && k % 4 == 0, "lm_pack_weight: bad args");
+  const long long total4 = n * k / 4;
+  lm_pack_weight_kernel<<<(unsigned)ceil_div(total4, 256), 256, 0, (cudaStream_t)stream>>>(w, total4, (uint4*)out);
+  g_launches++;
+  QB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int qb_lm_decode_layer_tc(float* x, int64_t B, int32_t hidden, int32_t heads, int32_t inter, const qb_half* wqkv,
+                                     const qb_half* wo, const qb_half* wgate, const qb_half* wup, const qb_half* wdown,
+                                     float* k_cache, float* v_cache, int32_t Lmax, const int32_t* pos, const float* rope_cos,
+                                     const float* rope_sin, float* q_buf, float* attn_buf, float* mlp_buf, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  QB_REQUIRE(B >= 1 && B <= 32, "lm_decode_layer_tc: batch must be 1..32 (got %lld)", (long long)B);
+  QB_REQUIRE(hidden == heads * 64 && hidden % 16 == 0 && inter % 16 == 0, "lm_decode_layer_tc: unsupported dims");
+  SkParams p = {};
+  p.B = (int)B; p.eps = 1e-6f; p.H = heads; p.Lmax = Lmax; p.pos = pos; p.rcos = rope_cos; p.rsin = rope_sin;
+  p.kc = k_cache; p.vc = v_cache;
+  // RMSNorm + QKV + RoPE + cache append
+  p.x = x; p.K = hidden; p.W = (const uint4*)wqkv; p.out = q_buf;
+  if (int e = launch_skinny<SK_QKV>(p, 3 * heads * 4, st)) return e;
+  QB_CHECK_CUDA(launch_pdl(lm_decode_attn2_kernel, dim3((unsigned)heads, (unsigned)B), dim3(256), 0, st, (const float*)q_buf,
+                           (const float*)k_cache, (const float*)v_cache, (int)heads, (int)Lmax, (const int*)pos, attn_buf));
+  // o_proj + residual
+  p.x = attn_buf; p.K = hidden; p.W = (const uint4*)wo; p.out = x; p.N = hidden;
+  if (int e = launch_skinny<SK_RESID>(p, hidden / 8, st)) return e;
+  // RMSNorm + gate/up + SwiGLU
+  p.x = x; p.K = hidden; p.W = (const uint4*)wgate; p.W2 = (const uint4*)wup; p.out = mlp_buf; p.N = inter;
+  if (int e = launch_skinny<SK_GATEUP>(p, inter / 8, st)) return e;
+  // down + residual
+  p.x = mlp_buf; p.K = inter; p.W = (const uint4*)wdown; p.W2 = nullptr; p.out = x; p.N = hidden;
+  if (int e = launch_skinny<SK_RESID>(p, hidden / 8, st)) return e;
+  return 0;
+}
+
+extern "C" int qb_lm_head_argmax_tc(const float* x, int64_t B, int32_t hidden, const qb_half* w_head, const int32_t* range,
+                                    int32_t max_cols, const float* embedding, float* x_next, int64_t* out_ids,
+                                    int32_t out_stride, int32_t* pos, int32_t* slot, float* part_val, int32_t* part_idx,
+                                    void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  QB_REQUIRE(B >= 1 && B <= 32 && max_cols % 16 == 0, "lm_head_argmax_tc: bad args (max_cols must be a multiple of 16)");
+  SkParams p = {};
+  p.B = (int)B; p.eps = 1e-6f; p.x = x; p.K = hidden; p.W = (const uint4*)w_head; p.range = range;
+  p.part_val = part_val; p.part_idx = part_idx;
+  if (int e = launch_skinny<SK_HEAD>(p, max_cols / 16, st)) return e;
+  QB_CHECK_CUDA(launch_pdl(lm_argmax_embed_kernel, dim3((unsigned)B), dim3(128), 0, st, (const float*)part_val,
+                           (const int*)part_idx, (int)(max_cols / 16), (int)B, embedding, (int)hidden, x_next, out_ids,
+                           (int)out_stride, (int*)pos, (int*)slot));
   return 0;
 }

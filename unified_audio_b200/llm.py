@@ -10,12 +10,14 @@ state_dict keys are the reference's (HF Llama layer names under `layers.*`, `nor
 condition encoder (`cond_*`, built but never executed: llm_sft.py:62-65,112-115) is accepted at load and ignored.
 
 Prefill / teacher-forced forward: tcgen05 GEMMs (3-term split) + causal split-precision flash attention over a static fp32 KV cache.
-Decode: fused skinny fp32 kernels, one CUDA graph per step replayed 33 + T times; greedy (do_sample=False, the shipped
+Decode: fused skinny kernels (3-term fp16-split mma.sync over pre-packed weights, programmatic dependent launch; the fp32
+SIMT versions are the cross-check, QB_LM_DECODE=simt), one CUDA graph per step replayed 33 + T times; greedy (do_sample=False, the shipped
 setting U/model/model.py:173).  No PyTorch / CPU fallback for the transformer stack.
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
+import os
 from typing import Optional
 
 import torch
@@ -86,6 +88,8 @@ class LLM_SFT(nn.Module):
         for name, child in tree.named_children():
             self.add_module(name, child)
         self._w, self._ws = None, {}
+        # "tc": packed fp16-split weights + mma.sync + programmatic dependent launch (product);  "simt": fp32 cross-check
+        self.decode_kernel = os.environ.get("QB_LM_DECODE", "tc")
         self.eval()
 
     # ------------------------------------------------------------------ state
@@ -125,6 +129,9 @@ class LLM_SFT(nn.Module):
                 wg32=(wg * sd[p + "post_attention_layernorm.weight"][None, :]).contiguous(),
                 wu32=(wu * sd[p + "post_attention_layernorm.weight"][None, :]).contiguous(),
                 wd32=sd[p + "mlp.down_proj.weight"].contiguous()))
+            L = layers[-1]       # product decode path: the same folded weights packed as fp16 {hi[4], lo[4]} groups
+            L.update(wqkv_p=ops.lm_pack_weight(L["wqkv32"]), wo_p=ops.lm_pack_weight(L["wo32"]), wg_p=ops.lm_pack_weight(L["wg32"]),
+                     wu_p=ops.lm_pack_weight(L["wu32"]), wd_p=ops.lm_pack_weight(L["wd32"]))
         inv = 1.0 / (10000.0 ** (torch.arange(0, 64, 2, dtype=torch.int64).float() / 64))
         fr = torch.arange(self.max_pos).float()[:, None] * inv[None, :]
         emb = torch.cat((fr, fr), -1)
@@ -132,6 +139,7 @@ class LLM_SFT(nn.Module):
                        head32=(sd["output_head.weight"] * sd["norm.weight"][None, :]).contiguous(), emb=sd["codec_embedding.weight"].contiguous(),
                        adapter=Planes.from_f32(sd["adapter.weight"], True), adapter_b=sd["adapter.bias"].contiguous(),
                        cos=emb.cos().to(dev).contiguous(), sin=emb.sin().to(dev).contiguous())
+        self._w["head_p"] = ops.lm_pack_weight(self._w["head32"])
         return self._w
 
     def _buf(self, name, shape, dtype=torch.float32):
@@ -180,9 +188,9 @@ class LLM_SFT(nn.Module):
         W = self._prepare()
         H, heads, inter = self.hidden, self.heads, 4 * self.hidden
         qb, ab, mb = self._buf("dq", (B, H)), self._buf("da", (B, H)), self._buf("dm", (B, inter))
+        layer = ops.lm_decode_layer_tc if self.decode_kernel == "tc" else ops.lm_decode_layer
         for i, Lw in enumerate(W["layers"]):
-            ops.lm_decode_layer(x, B, H, heads, inter, Lw, cache.k[i], cache.v[i], cache.Lmax, cache.pos, W["cos"], W["sin"],
-                                qb, ab, mb)
+            layer(x, B, H, heads, inter, Lw, cache.k[i], cache.v[i], cache.Lmax, cache.pos, W["cos"], W["sin"], qb, ab, mb)
 
     @torch.no_grad()
     def llm_forward(self, inputs_embeds, attention_mask=None, past_key_values: Optional[StaticKVCache] = None,
@@ -303,8 +311,12 @@ class LLM_SFT(nn.Module):
 
         def step():
             self._decode_layers(xs, B, cache)
-            ops.lm_head_argmax(xs, B, H, W["norm"], W["head32"], rng, max_cols, W["emb"], xs, out_ids, n_steps, cache.pos,
-                               slot, pv, pi)
+            if self.decode_kernel == "tc":
+                ops.lm_head_argmax_tc(xs, B, H, W["head_p"], rng, max_cols, W["emb"], xs, out_ids, n_steps, cache.pos, slot,
+                                      pv, pi)
+            else:
+                ops.lm_head_argmax(xs, B, H, W["norm"], W["head32"], rng, max_cols, W["emb"], xs, out_ids, n_steps, cache.pos,
+                                   slot, pv, pi)
 
         graph = None
         if use_graph:

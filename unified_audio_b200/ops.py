@@ -235,6 +235,26 @@ def lm_head_argmax(x, B, hidden, final_norm, w_head, rng, max_cols, emb, x_next,
                                              _stream()))
 
 
+def lm_pack_weight(w: torch.Tensor) -> torch.Tensor:
+    """fp32 [n,k] -> fp16 [n,2k] groups of {hi[4], lo[4]} (decode B-fragment layout, include/quark_b200.h)."""
+    w = w.float().contiguous()
+    n, k = w.shape
+    out = torch.empty(n, 2 * k, dtype=torch.float16, device=w.device)
+    _lib.check(_lib.load().qb_lm_pack_weight(_p(w), n, k, _p(out), _stream()))
+    return out
+
+
+def lm_decode_layer_tc(x, B, hidden, heads, inter, L, kc, vc, Lmax, pos, cos, sin, q_buf, attn_buf, mlp_buf):
+    _lib.check(_lib.load().qb_lm_decode_layer_tc(_p(x), B, hidden, heads, inter, _p(L["wqkv_p"]), _p(L["wo_p"]), _p(L["wg_p"]),
+                                                 _p(L["wu_p"]), _p(L["wd_p"]), _p(kc), _p(vc), Lmax, _p(pos), _p(cos), _p(sin),
+                                                 _p(q_buf), _p(attn_buf), _p(mlp_buf), _stream()))
+
+
+def lm_head_argmax_tc(x, B, hidden, w_head_p, rng, max_cols, emb, x_next, out_ids, out_stride, pos, slot, pv, pi):
+    _lib.check(_lib.load().qb_lm_head_argmax_tc(_p(x), B, hidden, _p(w_head_p), _p(rng), max_cols, _p(emb), _p(x_next),
+                                                _p(out_ids), out_stride, _p(pos), _p(slot), _p(pv), _p(pi), _stream()))
+
+
 def launch_count() -> int:
     return int(_lib.load().qb_launch_count())
 
