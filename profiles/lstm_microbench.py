@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from unified_audio_b200 import ops
-B, T, H = 64, 500, 1536
+B, T, H = (int(sys.argv[1]) if len(sys.argv) > 1 else 64), 500, 1536
 xp = torch.randn(B, T, 4 * H, device="cuda")
 whh = ops.Planes.from_f32((torch.rand(4 * H, H, device="cuda") * 2 - 1) / H ** 0.5, False)
 out = ops.Planes.zeros((B, T, H), False, "cuda")
