@@ -224,9 +224,19 @@ def run_lm(args):
         return
     from unified_audio_b200 import ops
     from unified_audio_b200.llm import LLM_SFT
+    from unified_audio_b200.parallel import gather_tokens
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:       # sequences are independent: B per rank (weak scaling), one all_gather of the generated ids
+        import torch.distributed as dist_
+        dist = dist_
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
     m = LLM_SFT(num_tasks=3, task_map=LM["task_map"], feats_dim=768, llm_base_config=LM["llm_base_config"]).to(dev)
     g = torch.Generator(device=dev).manual_seed(7)
     with torch.no_grad():
@@ -238,42 +248,64 @@ def run_lm(args):
             else:
                 p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g, device=dev))
     m._w = None
-    mix_h = torch.randn(B, T, 768).pin_memory()
+    mix_h = torch.randn(B, T, 768, generator=torch.Generator().manual_seed(100 + rank)).pin_memory()
     mix = mix_h.to(dev)
+
+    def step(src):
+        gi, si = m.generate("se", None, None, src, src, do_sample=False)
+        if dist is not None:
+            gather_tokens(torch.cat([gi, si], 1), world * B)
+        return gi, si
+
+    def timed(fn):
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
     for _ in range(max(args.warmup, 1)):
-        m.generate("se", None, None, mix, mix, do_sample=False)
+        step(mix)
     ops.launch_count_reset()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(); e0.record()
-    for _ in range(args.steps):
-        m.generate("se", None, None, mix, mix, do_sample=False)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
+    ms = timed(lambda: step(mix))
     launches = ops.launch_count() // args.steps
-    e0.record()
-    for _ in range(args.steps):
-        gi, si = m.generate("se", None, None, mix_h.to(dev, non_blocking=True), mix_h.to(dev, non_blocking=True), do_sample=False)
+
+    def e2e_step():
+        gi, si = step(mix_h.to(dev, non_blocking=True))
         gi.cpu(); si.cpu()
-    e1.record(); torch.cuda.synchronize()
-    ms_e2e = e0.elapsed_time(e1) / args.steps
+    ms_e2e = timed(e2e_step)
+    B = B * world                       # whole-job totals from here on
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     peaks = load_peaks()
     # bytes per decode step: fp32 layer weights + head slice + fp32 KV read, summed over the 283 steps
     w_bytes = 12 * (4 * 512 * 512 + 3 * 512 * 2048) * 4
     kv = sum(B * 2 * 12 * 512 * 4 * (252 + i + 1) for i in range(283))
     head = 33 * 4096 * 512 * 4 + 250 * 8192 * 512 * 4
-    total_bytes = 283 * w_bytes + head + kv
+    total_bytes = world * (283 * w_bytes + head) + kv      # every rank streams its replica of the weights
     gbs = total_bytes / (ms * 1e-3) / 1e9
-    print(json.dumps(dict(metric="unise_sr_arlm_generate_tokens_per_s", value=B * 283 / (ms * 1e-3), unit="tokens/s", n_gpus=1,
+    print(json.dumps(dict(metric="unise_sr_arlm_generate_tokens_per_s", value=B * 283 / (ms * 1e-3), unit="tokens/s", n_gpus=world,
                           steps=args.steps, warmup=max(args.warmup, 1), ms_per_step=ms, higher_is_better=True, scaling="weak",
                           vs_baseline=None, dtype="f16x3 split tensor-core (fp32-grade), f32 accumulate / f32 KV cache", data="synthetic",
-                          config=dict(workload="UniSE SR AR-LM greedy generate (prefill 252 + 33 + 250 cached steps), batch=32",
-                                      batch=B, semantic_length=T),
-                          e2e=dict(value=B * 283 / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=int(mix_h.numel() * 4),
+                          config=dict(workload="UniSE SR AR-LM greedy generate (prefill 252 + 33 + 250 cached steps), batch=32 per GPU",
+                                      batch=B, semantic_length=T, parallelism=f"dp{world} (sequences sharded, one NCCL all_gather of ids)",
+                                      launches="decode steps replay one captured CUDA graph (62 kernels); gpu_launches counts eager launches + the capture"),
+                          e2e=dict(value=B * 283 / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=int(mix_h.numel() * 4) * world,
                                    d2h_bytes_per_step=B * 282 * 8),
                           gpu_launches=int(launches),
-                          roofline=dict(bound="hbm", achieved=gbs, peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"],
+                          roofline=dict(bound="hbm", achieved=gbs, peak=peaks["hbm"] * world, unit="GB/s", frac=gbs / (peaks["hbm"] * world),
                                         traffic=None, kernel="decode step (lm_skinny<QKV|RESID|GATEUP|HEAD> + lm_decode_attn2), algorithmic bytes = 4 B/param packed "
                                         "weights + head slice + fp32 KV read per step, whole generate incl. prefill"))))
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def main():

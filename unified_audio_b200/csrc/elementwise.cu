@@ -3,6 +3,8 @@
 // 128-bit vector accesses along C, one warp (or block) per row, fp32 statistics (two-pass).
 #include <atomic>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "quark_b200.h"
 
@@ -133,14 +135,15 @@ __global__ void dwconv7_ln_kernel(const float* __restrict__ x, const float* __re
 // v2: block = (TT consecutive frames of one clip) x (all channels); one thread owns 4 channels
 // (float4 along C => fully coalesced 16 B accesses) and slides a 7-row register window over time, so
 // each input row is read once per block (halo re-reads hit L2).  LayerNorm statistics for the TT rows
-// are block-reduced together (two-pass: mean, then centred variance).
-template <int TT>
-__global__ void __launch_bounds__(512)
+// are block-reduced together in one round (equal-count (mean, M2) merges, see below).  <= 85 registers at 384 threads keeps
+// two CTAs per SM: a 768-thread one-CTA-per-SM variant with all loads hoisted measured 1.7x SLOWER (barrier stalls idle the SM).
+template <int TT, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 dwconv7_ln_v2_kernel(const float4* __restrict__ x, const float* __restrict__ dw_w, const float4* __restrict__ dw_b,
                      const float4* __restrict__ ln_w, const float4* __restrict__ ln_b, int T, int C4,
                      __half* __restrict__ hi, __half* __restrict__ lo) {
-  __shared__ float red[16][TT];
-  __shared__ float tot[TT];
+  __shared__ float red[16][TT], red2[16][TT];
+  __shared__ float tot[TT], tot2[TT];
   const int b = blockIdx.y, t0 = blockIdx.x * TT, c4 = threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   float w[28];
@@ -178,40 +181,42 @@ dwconv7_ln_v2_kernel(const float4* __restrict__ x, const float* __restrict__ dw_
 #pragma unroll
     for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
   }
-  const float invC = 1.f / (4.f * C4);
+  // LayerNorm statistics in ONE block round: every thread starts from the exact (mean, M2) of its 4 channels and
+  // equal-count partials are merged pairwise (Chan et al.): m = (ma + mb)/2, M2 = M2a + M2b + (mb - ma)^2 * n/2 -
+  // a centred variance (no E[x^2] - mean^2 cancellation) without a second pass over the block.
   float mean[TT], rstd[TT];
-  // pass 1: means
 #pragma unroll
   for (int i = 0; i < TT; ++i) {
-    float s = warp_sum(y[i].x + y[i].y + y[i].z + y[i].w);
-    if (lane == 0) red[warp][i] = s;
+    float m = 0.25f * ((y[i].x + y[i].y) + (y[i].z + y[i].w));
+    const float dx = y[i].x - m, dy = y[i].y - m, dz = y[i].z - m, dw = y[i].w - m;
+    float q = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    float n_half = 2.f;                       // n/2 for partials of n = 4 values
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float mo = __shfl_xor_sync(0xffffffffu, m, o), qo = __shfl_xor_sync(0xffffffffu, q, o);
+      const float d = mo - m;
+      q = q + qo + d * d * n_half;
+      m = 0.5f * (m + mo);
+      n_half *= 2.f;
+    }
+    if (lane == 0) { red[warp][i] = m; red2[warp][i] = q; }
   }
   __syncthreads();
-  if (threadIdx.x < TT) {
-    float s = 0.f;
-    for (int wv = 0; wv < nwarps; ++wv) s += red[wv][threadIdx.x];
-    tot[threadIdx.x] = s * invC;
+  if (threadIdx.x < TT) {                     // merge the warps' partials (128 values each) sequentially
+    float m = red[0][threadIdx.x], q = red2[0][threadIdx.x], n = 128.f;
+    for (int wv = 1; wv < nwarps; ++wv) {
+      const float mo = red[wv][threadIdx.x], qo = red2[wv][threadIdx.x];
+      const float d = mo - m, nt = n + 128.f;
+      q = q + qo + d * d * (n * 128.f / nt);
+      m = m + d * (128.f / nt);
+      n = nt;
+    }
+    tot[threadIdx.x] = m;
+    tot2[threadIdx.x] = rsqrtf(q / n + 1e-6f);
   }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < TT; ++i) mean[i] = tot[i];
-  __syncthreads();
-  // pass 2: centred variance
-#pragma unroll
-  for (int i = 0; i < TT; ++i) {
-    const float dx = y[i].x - mean[i], dy = y[i].y - mean[i], dz = y[i].z - mean[i], dw = y[i].w - mean[i];
-    float s = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw);
-    if (lane == 0) red[warp][i] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x < TT) {
-    float s = 0.f;
-    for (int wv = 0; wv < nwarps; ++wv) s += red[wv][threadIdx.x];
-    tot[threadIdx.x] = rsqrtf(s * invC + 1e-6f);
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < TT; ++i) rstd[i] = tot[i];
+  for (int i = 0; i < TT; ++i) { mean[i] = tot[i]; rstd[i] = tot2[i]; }
   const float4 lw = ln_w[c4], lb = ln_b[c4];
 #pragma unroll
   for (int i = 0; i < TT; ++i) {
@@ -428,9 +433,14 @@ extern "C" int qb_dwconv7_ln(const float* x, const float* dw_w, const float* dw_
   if (C % 128 == 0 && C / 4 <= 512) {
     constexpr int TT = 8;
     dim3 grid((unsigned)ceil_div(T, TT), (unsigned)B);
-    dwconv7_ln_v2_kernel<TT><<<grid, (unsigned)(C / 4), 0, (cudaStream_t)stream>>>(
-        (const float4*)x, dw_w, (const float4*)dw_b, (const float4*)ln_w, (const float4*)ln_b, (int)T, (int)(C / 4),
-        (__half*)hi, (__half*)lo);
+    if (C / 4 <= 384)      // <= 85 registers: two CTAs per SM, one's loads overlap the other's reduction / stores
+      dwconv7_ln_v2_kernel<TT, 384, 2><<<grid, (unsigned)(C / 4), 0, (cudaStream_t)stream>>>(
+          (const float4*)x, dw_w, (const float4*)dw_b, (const float4*)ln_w, (const float4*)ln_b, (int)T, (int)(C / 4),
+          (__half*)hi, (__half*)lo);
+    else
+      dwconv7_ln_v2_kernel<TT, 512, 1><<<grid, (unsigned)(C / 4), 0, (cudaStream_t)stream>>>(
+          (const float4*)x, dw_w, (const float4*)dw_b, (const float4*)ln_w, (const float4*)ln_b, (int)T, (int)(C / 4),
+          (__half*)hi, (__half*)lo);
     QB_LAUNCH_END();
   }
   const int warps = 8;
