@@ -567,6 +567,7 @@ struct SkParams {
   const int* range;
   float* part_val;
   int* part_idx;
+  int pdl_early;         // 1: release the dependent grid before the dependency wait (deep pile-up), 0: after the K loop
 };
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -625,7 +626,7 @@ lm_skinny_kernel(const SkParams p) {
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) wv[nt][s] = ok ? __ldg(wrow[nt] + step * 4 + t) : make_uint4(0u, 0u, 0u, 0u);
   }
-  pdl_launch_dependents();
+  if (p.pdl_early) pdl_launch_dependents();
   pdl_wait();
   float acc[2][NT][4];
 #pragma unroll
@@ -674,6 +675,8 @@ lm_skinny_kernel(const SkParams p) {
         }
     }
   }
+  // the dependent grid may start (and prefetch its weights) while this one reduces, stores and drains
+  if (!p.pdl_early) pdl_launch_dependents();
   // ---- cross-warp reduction (fixed order)
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
@@ -757,10 +760,10 @@ lm_skinny_kernel(const SkParams p) {
 // (max, sum, acc) triples are merged through shared memory in a fixed order.  No score buffer: any cache length.
 __global__ void __launch_bounds__(256)
 lm_decode_attn2_kernel(const float* __restrict__ q, const float* __restrict__ kc, const float* __restrict__ vc, int H,
-                       int Lmax, const int* __restrict__ posp, float* __restrict__ out) {
+                       int Lmax, const int* __restrict__ posp, float* __restrict__ out, int pdl_early) {
   __shared__ __align__(16) float sacc[16][64];
   __shared__ float sm[16], sl[16];
-  pdl_launch_dependents();
+  if (pdl_early) pdl_launch_dependents();
   pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = lane & 15, hw = warp * 2 + (lane >> 4);
@@ -805,6 +808,7 @@ lm_decode_attn2_kernel(const float* __restrict__ q, const float* __restrict__ kc
       m = mn;
     }
   }
+  if (!pdl_early) pdl_launch_dependents();
   *reinterpret_cast<float4*>(&sacc[hw][4 * c]) = acc;
   if (c == 0) { sm[hw] = m; sl[hw] = l; }
   __syncthreads();
@@ -929,6 +933,14 @@ extern "C" int qb_lm_head_argmax(const float* x, int64_t B, int32_t hidden, cons
 }
 
 // ------------------------------------------------------------------------------------------ tensor-core decode (product path)
+static int lm_pdl_early() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("QB_LM_PDL_EARLY");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
 static bool lm_pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -980,12 +992,13 @@ extern "C" int qb_lm_decode_layer_tc(float* x, int64_t B, int32_t hidden, int32_
   QB_REQUIRE(hidden == heads * 64 && hidden % 16 == 0 && inter % 16 == 0, "lm_decode_layer_tc: unsupported dims");
   SkParams p = {};
   p.B = (int)B; p.eps = 1e-6f; p.H = heads; p.Lmax = Lmax; p.pos = pos; p.rcos = rope_cos; p.rsin = rope_sin;
-  p.kc = k_cache; p.vc = v_cache;
+  p.kc = k_cache; p.vc = v_cache; p.pdl_early = lm_pdl_early();
   // RMSNorm + QKV + RoPE + cache append
   p.x = x; p.K = hidden; p.W = (const uint4*)wqkv; p.out = q_buf;
   if (int e = launch_skinny<SK_QKV>(p, 3 * heads * 4, st)) return e;
   QB_CHECK_CUDA(launch_pdl(lm_decode_attn2_kernel, dim3((unsigned)heads, (unsigned)B), dim3(256), 0, st, (const float*)q_buf,
-                           (const float*)k_cache, (const float*)v_cache, (int)heads, (int)Lmax, (const int*)pos, attn_buf));
+                           (const float*)k_cache, (const float*)v_cache, (int)heads, (int)Lmax, (const int*)pos, attn_buf,
+                           lm_pdl_early()));
   // o_proj + residual
   p.x = attn_buf; p.K = hidden; p.W = (const uint4*)wo; p.out = x; p.N = hidden;
   if (int e = launch_skinny<SK_RESID>(p, hidden / 8, st)) return e;
@@ -1006,7 +1019,7 @@ extern "C" int qb_lm_head_argmax_tc(const float* x, int64_t B, int32_t hidden, c
   QB_REQUIRE(B >= 1 && B <= 32 && max_cols % 16 == 0, "lm_head_argmax_tc: bad args (max_cols must be a multiple of 16)");
   SkParams p = {};
   p.B = (int)B; p.eps = 1e-6f; p.x = x; p.K = hidden; p.W = (const uint4*)w_head; p.range = range;
-  p.part_val = part_val; p.part_idx = part_idx;
+  p.part_val = part_val; p.part_idx = part_idx; p.pdl_early = lm_pdl_early();
   if (int e = launch_skinny<SK_HEAD>(p, max_cols / 16, st)) return e;
   QB_CHECK_CUDA(launch_pdl(lm_argmax_embed_kernel, dim3((unsigned)B), dim3(128), 0, st, (const float*)part_val,
                            (const int*)part_idx, (int)(max_cols / 16), (int)B, embedding, (int)hidden, x_next, out_ids,

@@ -90,17 +90,19 @@ class LLM_SFT(nn.Module):
         self._w, self._ws = None, {}
         # "tc": packed fp16-split weights + mma.sync + programmatic dependent launch (product);  "simt": fp32 cross-check
         self.decode_kernel = os.environ.get("QB_LM_DECODE", "tc")
+        self.graph_steps = int(os.environ.get("QB_LM_GRAPH_STEPS", "8"))     # decode steps per replayed CUDA graph
+        self._gen_state = {}
         self.eval()
 
     # ------------------------------------------------------------------ state
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         sd = {k: v for k, v in state_dict.items() if not k.startswith(("cond_", "rotary_emb."))}
         r = super().load_state_dict(sd, strict=strict, assign=assign)
-        self._w = None
+        self._w, self._gen_state = None, {}          # captured graphs point at the old prepared weights
         return r
 
     def _apply(self, fn, *a, **k):
-        self._w, self._ws = None, {}
+        self._w, self._ws, self._gen_state = None, {}, {}
         return super()._apply(fn, *a, **k)
 
     def _dev(self):
@@ -298,16 +300,27 @@ class LLM_SFT(nn.Module):
         B, P, H = prefix.shape
         n_steps = global_length + 1 + semantic_length
         Lmax = -(-(P + n_steps) // 64) * 64
-        cache = StaticKVCache(self.n_layers, B, self.heads, Lmax, dev)
+        max_cols = max(self.global_size, self.semantic_size)
+        # Decode state (KV cache, counters, output ids) and the captured graphs are kept per shape: capturing and
+        # instantiating ~560 kernel nodes costs the host 10-50 ms, as much as the whole generation takes on the device.
+        key = (B, P, n_steps, bool(use_graph), self.decode_kernel, int(self.graph_steps), str(dev))
+        st = self._gen_state.get(key)
+        if st is None:
+            self._gen_state.clear()                    # one shape at a time (the cache is ~0.9 GB at B=32)
+            st = dict(cache=StaticKVCache(self.n_layers, B, self.heads, Lmax, dev),
+                      xs=torch.zeros(B, H, device=dev),
+                      rng=torch.zeros(2, dtype=torch.int32, device=dev), slot=torch.zeros(2, dtype=torch.int32, device=dev),
+                      out_ids=torch.zeros(B, n_steps, dtype=torch.int64, device=dev),
+                      pv=torch.zeros(max_cols // 16 + 1, 32, device=dev),
+                      pi=torch.zeros(max_cols // 16 + 1, 32, dtype=torch.int32, device=dev), g1=None, gk=None, captured=False)
+            self._gen_state[key] = st
+        cache, xs, rng, slot, out_ids, pv, pi = (st[k] for k in ("cache", "xs", "rng", "slot", "out_ids", "pv", "pi"))
+        cache.length = 0
+        cache.pos.zero_()
+        slot.zero_()
+        rng.copy_(torch.tensor([self.global_offset, self.global_offset + self.global_size], dtype=torch.int32), non_blocking=True)
         x = prefix.reshape(B * P, H).contiguous().clone()
         self._prefill(x, B, P, cache)
-        max_cols = max(self.global_size, self.semantic_size)
-        xs = self._buf("gx", (B, H))
-        rng = torch.tensor([self.global_offset, self.global_offset + self.global_size], dtype=torch.int32, device=dev)
-        slot = torch.zeros(2, dtype=torch.int32, device=dev)
-        out_ids = torch.zeros(B, n_steps, dtype=torch.int64, device=dev)
-        pv = self._buf("pv", (max_cols // 16 + 1, 32))
-        pi = self._buf("pi", (max_cols // 16 + 1, 32), torch.int32)
 
         def step():
             self._decode_layers(xs, B, cache)
@@ -318,28 +331,42 @@ class LLM_SFT(nn.Module):
                 ops.lm_head_argmax(xs, B, H, W["norm"], W["head32"], rng, max_cols, W["emb"], xs, out_ids, n_steps, cache.pos,
                                    slot, pv, pi)
 
-        graph = None
-        if use_graph:
+        # All decode state is on the device, so a graph may hold any number of consecutive steps: one single-step graph
+        # plus one of `graph_steps` steps (fewer replays per generation).
+        K = max(1, int(self.graph_steps))
+        if use_graph and not st["captured"]:
             # warm-up outside capture (one-time cudaFuncSetAttribute calls), then restore the mutated state
             xs.copy_(W["emb"][self.global_sos_token_id][None].expand(B, H))
             step()
-            cache.pos.fill_(cache.length)
-            slot.zero_()
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            st["g1"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(st["g1"]):
                 step()
+            if K > 1 and n_steps >= K:
+                st["gk"] = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(st["gk"]):
+                    for _ in range(K):
+                        step()
+            st["captured"] = True
             cache.pos.fill_(cache.length)
             slot.zero_()
-        run = graph.replay if graph is not None else step
+        g1, gk = (st["g1"], st["gk"]) if use_graph else (None, None)
+
+        def run(n):
+            while n > 0:
+                if gk is not None and n >= K:
+                    gk.replay()
+                    n -= K
+                else:
+                    g1.replay() if g1 is not None else step()
+                    n -= 1
+
         xs.copy_(W["emb"][self.global_sos_token_id][None].expand(B, H))
-        for _ in range(global_length + 1):
-            run()
-        rng.copy_(torch.tensor([self.semantic_offset, self.semantic_offset + self.semantic_size], dtype=torch.int32, device=dev))
+        run(global_length + 1)
+        rng.copy_(torch.tensor([self.semantic_offset, self.semantic_offset + self.semantic_size], dtype=torch.int32))
         xs.copy_(W["emb"][self.semantic_sos_token_id][None].expand(B, H))
-        for _ in range(semantic_length):
-            run()
+        run(semantic_length)
         cache.length += n_steps
-        global_ids = out_ids[:, :global_length] - self.global_offset
+        global_ids = out_ids[:, :global_length] - self.global_offset          # (new tensors: out_ids is reused by the next call)
         semantic_ids = out_ids[:, global_length + 1:] - self.semantic_offset
         return global_ids, semantic_ids
