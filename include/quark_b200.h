@@ -40,7 +40,7 @@ int64_t qb_launch_count(void);
 void qb_launch_count_reset(void);
 
 /* activation codes for the GEMM epilogue */
-enum { QB_ACT_NONE = 0, QB_ACT_GELU = 1, QB_ACT_SWIGLU = 2, QB_ACT_ELU = 3 };
+enum { QB_ACT_NONE = 0, QB_ACT_GELU = 1, QB_ACT_SWIGLU = 2, QB_ACT_ELU = 3, QB_ACT_TANH = 4 };
 
 /* Row mapping of an output / residual tensor: GEMM row (batch b, row m) lives at
  * ptr + ((b * rows_per_batch + row_off + m) * ld + n).  Lets a GEMM write straight into the
@@ -53,8 +53,10 @@ typedef struct {
 } qb_rowmap;
 
 /*
- * One dense contraction  D[b, m, n] = sum_{tap, c} A[b, m*stride + tap, c] * W[n, tap*a_ld + c]
- * i.e. nn.Linear (taps = stride = 1) or a strided nn.Conv1d over a zero-padded channel-last buffer
+ * One dense contraction  D[b, m, n] = sum_{tap, c} A[b, m*stride + tap*dilation, c] * W[n, tap*a_ld + c]
+ * i.e. nn.Linear (taps = stride = 1), a strided / dilated nn.Conv1d over a zero-padded channel-last buffer, or a
+ * ConvTranspose1d (stride s, kernel k) as ceil(k/s) taps producing all s output phases as s*Cout columns
+ * (bicodec/modules/encoder_decoder/wave_generator.py:42-48; weights repacked per phase at load)
  * (vq/conv.py:35-57, vq/semantic_module.py:13-52; weights repacked [Cout, k*Cin_pad] at load).
  * Epilogue:  v = acc + bias[n];  v = act(v);  v *= gamma[n];  v += residual[b,m,n];
  *            out_f32 <- v;   out planes <- split_fp16(act2(v))
@@ -81,6 +83,8 @@ typedef struct {
   qb_rowmap out_f32;        /* ptr NULL => not written */
   qb_rowmap out_hi;         /* fp16 planes; ptr NULL => not written */
   qb_rowmap out_lo;         /* ptr NULL => hi only (same ld / mapping fields as out_hi required) */
+  int32_t dilation;         /* tap spacing in input rows: A[b, m*stride + tap*dilation, c]; 0 or 1 = dense taps.
+                             * (DAC residual units, bicodec/modules/blocks/layers.py:52-60: k=7, dilation 1/3/9) */
 } qb_gemm_desc;
 
 /* tcgen05 / TMA / TMEM persistent GEMM (the product path). */
@@ -111,6 +115,20 @@ int qb_rmsnorm(const float* x, const float* w, float eps, int64_t rows, int64_t 
  * (vq/conv.py:201-204).  x [B, T, C] fp32; dw_w [C,7]; dw_b [C]. */
 int qb_dwconv7_ln(const float* x, const float* dw_w, const float* dw_b, const float* ln_w, const float* ln_b,
                   int64_t B, int64_t T, int64_t C, qb_half* hi, qb_half* lo, void* stream);
+/* AdaLayerNorm variants (bicodec/modules/blocks/vocos.py:88-111): LayerNorm(1e-6) without affine, then
+ * * scale[b, :] + shift[b, :] with per-clip rows `cond_stride` floats apart (scale / shift = Linear(d_vector)). */
+int qb_dwconv7_adaln(const float* x, const float* dw_w, const float* dw_b, const float* scale, const float* shift,
+                     int64_t cond_stride, int64_t B, int64_t T, int64_t C, qb_half* hi, qb_half* lo, void* stream);
+int qb_adalayernorm(const float* x, const float* scale, const float* shift, int64_t cond_stride, float eps, int64_t B,
+                    int64_t rows, int64_t C, float* out_f32, qb_half* hi, qb_half* lo, int64_t ld,
+                    int64_t rows_per_batch, int64_t row_off, void* stream);
+/* Snake activation x + sin(alpha x)^2 / (alpha + 1e-9) per channel (bicodec/modules/blocks/layers.py:33-44) of fp32
+ * rows [B, T, C] (clip b at x + b * x_batch_stride) -> planes in a padded buffer; channels C..ld-1 zeroed. */
+int qb_snake_planes(const float* x, int64_t x_batch_stride, const float* alpha, int64_t B, int64_t T, int64_t C,
+                    qb_half* hi, qb_half* lo, int64_t ld, int64_t rows_per_batch, int64_t row_off, void* stream);
+/* x[b,t,:] + vec[b,:] -> planes (prenet output + speaker d-vector, bicodec/bicodec.py:196-197). */
+int qb_addvec_planes(const float* x, const float* vec, int64_t B, int64_t T, int64_t C, qb_half* hi, qb_half* lo,
+                     int64_t ld, int64_t rows_per_batch, int64_t row_off, void* stream);
 /* GroupNorm(32 groups, eps) statistics then apply (+ optional swish): vq/conv.py:261,286-300.
  * x [B,T,C] fp32; stats [B,32,2] (mean, rstd).  Output fp32 and/or planes into a padded buffer. */
 int qb_groupnorm_stats(const float* x, int64_t B, int64_t T, int64_t C, int32_t groups, float eps, float* stats,

@@ -171,7 +171,7 @@ def test_gemm_desc_struct_layout_matches_header():
     assert C.sizeof(RowMap) == 32
     assert GemmDesc.taps.offset == 40 and GemmDesc.stride.offset == 44 and GemmDesc.m_per_batch.offset == 48
     assert GemmDesc.residual.offset == 96 and GemmDesc.act.offset == 128 and GemmDesc.out_f32.offset == 136
-    assert C.sizeof(GemmDesc) == 136 + 3 * 32
+    assert GemmDesc.dilation.offset == 136 + 3 * 32 and C.sizeof(GemmDesc) == 136 + 3 * 32 + 8
 
 
 def test_bench_reference_arm_contract():
@@ -184,3 +184,23 @@ def test_bench_reference_arm_contract():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def test_bicodec_oracle_matches_reference_fixture_and_spec_keys():
+    """oracle/bicodec.py reproduces the committed outputs of the reference's BiCodec classes (CPU fp32), and the product's
+    state-dict layout is the reference's (tests/golden/bicodec_keys.json, dumped from the reference modules)."""
+    import numpy as np
+    from oracle import bicodec as ob
+    from unified_audio_b200.bicodec import BICODEC_CONFIG, bicodec_spec
+    z = np.load(os.path.join(GOLD, "bicodec_small.npz"))
+    meta = json.loads(str(z["meta"]))
+    cfg = ob.bicodec_small()
+    sd = ob.make_state_dict(cfg, meta["seed"])
+    wav = ob.detokenize(sd, cfg, torch.from_numpy(z["semantic"]), torch.from_numpy(z["global_tokens"]))
+    want = torch.from_numpy(z["wav"])
+    assert float((wav - want).abs().max() / want.abs().max()) < 1e-5
+    keys = json.load(open(os.path.join(GOLD, "bicodec_keys.json")))
+    assert BICODEC_CONFIG == ob.BICODEC_FULL
+    spec = {k: list(v) for k, v in bicodec_spec(BICODEC_CONFIG).items()}
+    assert spec == keys
+    assert {k: list(v[0]) for k, v in ob.param_specs(ob.BICODEC_FULL).items()} == keys

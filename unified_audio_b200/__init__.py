@@ -4,6 +4,8 @@ Public surface mirrors the reference (alibaba/unified-audio):
   Codec            <- QuarkAudio-HCodec/HCodec-2.0/vq/codec.py:17   (encode / decode)
   ResidualVQ       <- vector_quantize_pytorch.ResidualVQ as the reference constructs it
   LLM_SFT          <- QuarkAudio-UniSE/model/llm/llm_sft.py:13 (llm_forward / forward / generate)
+  CodecH1          <- QuarkAudio-HCodec/HCodec-1.0/vq/codec.py:21   (encode / decode)
+  BiCodec          <- QuarkAudio-UniSE/model/bicodec/bicodec.py:182 (detokenize)
 Kernels live in csrc/ behind the C ABI of include/quark_b200.h (lib/libquark_b200.so).
 """
 __version__ = "0.1.0"
@@ -12,3 +14,4 @@ from .codec import Codec  # noqa: E402,F401
 from .codec_h1 import CodecH1  # noqa: E402,F401
 from .rvq import ResidualVQ  # noqa: E402,F401
 from .llm import LLM_SFT  # noqa: E402,F401
+from .bicodec import BiCodec  # noqa: E402,F401

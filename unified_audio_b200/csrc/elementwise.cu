@@ -63,7 +63,7 @@ __global__ void bct_to_planes_kernel(const float* __restrict__ x, int C, int T, 
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bz,
                                  float eps, long long rows_total, int rows, int C, float* __restrict__ out,
                                  __half* __restrict__ hi, __half* __restrict__ lo, long long ld, long long rpb,
-                                 long long off) {
+                                 long long off, long long wb_bstride) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows_total) return;
@@ -76,6 +76,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   const float rstd = rsqrtf(warp_sum(q) / C + eps);
   const long long b = row / rows, r = row % rows;
   const long long o = (b * rpb + off + r) * ld;
+  w += b * wb_bstride;            // AdaLayerNorm: per-clip scale / shift rows (stride 0 = ordinary affine LayerNorm)
+  bz += b * wb_bstride;
   for (int c = lane; c < C; c += 32) {
     float v = (xr[c] - mean) * rstd * w[c] + bz[c];
     if (out) out[row * C + c] = v;
@@ -105,7 +107,7 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restr
 __global__ void dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ dw_w,
                                   const float* __restrict__ dw_b, const float* __restrict__ ln_w,
                                   const float* __restrict__ ln_b, int T, int C, long long rows_total,
-                                  __half* __restrict__ hi, __half* __restrict__ lo) {
+                                  __half* __restrict__ hi, __half* __restrict__ lo, long long ln_bstride) {
   extern __shared__ float sm[];
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + wi;
@@ -129,6 +131,8 @@ __global__ void dwconv7_ln_kernel(const float* __restrict__ x, const float* __re
   float q = 0.f;
   for (int c = lane; c < C; c += 32) { float d = y[c] - mean; q += d * d; }
   const float rstd = rsqrtf(warp_sum(q) / C + 1e-6f);
+  ln_w += (row / T) * ln_bstride;      // per-clip scale / shift (AdaLayerNorm) when the stride is non-zero
+  ln_b += (row / T) * ln_bstride;
   for (int c = lane; c < C; c += 32) store_planes(hi, lo, row * C + c, (y[c] - mean) * rstd * ln_w[c] + ln_b[c]);
 }
 
@@ -141,7 +145,7 @@ template <int TT, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 dwconv7_ln_v2_kernel(const float4* __restrict__ x, const float* __restrict__ dw_w, const float4* __restrict__ dw_b,
                      const float4* __restrict__ ln_w, const float4* __restrict__ ln_b, int T, int C4,
-                     __half* __restrict__ hi, __half* __restrict__ lo) {
+                     __half* __restrict__ hi, __half* __restrict__ lo, long long ln_bstride4) {
   __shared__ float red[16][TT], red2[16][TT];
   __shared__ float tot[TT], tot2[TT];
   const int b = blockIdx.y, t0 = blockIdx.x * TT, c4 = threadIdx.x;
@@ -217,7 +221,7 @@ dwconv7_ln_v2_kernel(const float4* __restrict__ x, const float* __restrict__ dw_
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < TT; ++i) { mean[i] = tot[i]; rstd[i] = tot2[i]; }
-  const float4 lw = ln_w[c4], lb = ln_b[c4];
+  const float4 lw = ln_w[b * ln_bstride4 + c4], lb = ln_b[b * ln_bstride4 + c4];     // stride 0: static affine
 #pragma unroll
   for (int i = 0; i < TT; ++i) {
     const int t = t0 + i;
@@ -414,7 +418,19 @@ extern "C" int qb_layernorm(const float* x, const float* w, const float* b, floa
   QB_REQUIRE(!hi || (C <= ld && row_off + rows <= rows_per_batch), "layernorm: plane buffer too small");
   const long long total = B * rows;
   layernorm_kernel<<<(unsigned)ceil_div(total, 8), 256, 0, (cudaStream_t)stream>>>(
-      x, w, b, eps, total, (int)rows, (int)C, out_f32, (__half*)hi, (__half*)lo, ld, rows_per_batch, row_off);
+      x, w, b, eps, total, (int)rows, (int)C, out_f32, (__half*)hi, (__half*)lo, ld, rows_per_batch, row_off, 0);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_adalayernorm(const float* x, const float* scale, const float* shift, int64_t cond_stride, float eps,
+                               int64_t B, int64_t rows, int64_t C, float* out_f32, qb_half* hi, qb_half* lo, int64_t ld,
+                               int64_t rows_per_batch, int64_t row_off, void* stream) {
+  QB_REQUIRE(x && scale && shift && (out_f32 || hi), "adalayernorm: bad args");
+  QB_REQUIRE(!hi || (C <= ld && row_off + rows <= rows_per_batch), "adalayernorm: plane buffer too small");
+  const long long total = B * rows;
+  layernorm_kernel<<<(unsigned)ceil_div(total, 8), 256, 0, (cudaStream_t)stream>>>(
+      x, scale, shift, eps, total, (int)rows, (int)C, out_f32, (__half*)hi, (__half*)lo, ld, rows_per_batch, row_off,
+      cond_stride);
   QB_LAUNCH_END();
 }
 
@@ -426,21 +442,20 @@ extern "C" int qb_rmsnorm(const float* x, const float* w, float eps, int64_t row
   QB_LAUNCH_END();
 }
 
-extern "C" int qb_dwconv7_ln(const float* x, const float* dw_w, const float* dw_b, const float* ln_w,
-                             const float* ln_b, int64_t B, int64_t T, int64_t C, qb_half* hi, qb_half* lo,
-                             void* stream) {
+static int dwconv7_ln_launch(const float* x, const float* dw_w, const float* dw_b, const float* ln_w, const float* ln_b,
+                             int64_t ln_bstride, int64_t B, int64_t T, int64_t C, qb_half* hi, qb_half* lo, void* stream) {
   QB_REQUIRE(x && dw_w && dw_b && ln_w && ln_b && hi, "dwconv7_ln: bad args");
-  if (C % 128 == 0 && C / 4 <= 512) {
+  if (C % 128 == 0 && C / 4 <= 512 && ln_bstride % 4 == 0) {
     constexpr int TT = 8;
     dim3 grid((unsigned)ceil_div(T, TT), (unsigned)B);
     if (C / 4 <= 384)      // <= 85 registers: two CTAs per SM, one's loads overlap the other's reduction / stores
       dwconv7_ln_v2_kernel<TT, 384, 2><<<grid, (unsigned)(C / 4), 0, (cudaStream_t)stream>>>(
           (const float4*)x, dw_w, (const float4*)dw_b, (const float4*)ln_w, (const float4*)ln_b, (int)T, (int)(C / 4),
-          (__half*)hi, (__half*)lo);
+          (__half*)hi, (__half*)lo, (long long)(ln_bstride / 4));
     else
       dwconv7_ln_v2_kernel<TT, 512, 1><<<grid, (unsigned)(C / 4), 0, (cudaStream_t)stream>>>(
           (const float4*)x, dw_w, (const float4*)dw_b, (const float4*)ln_w, (const float4*)ln_b, (int)T, (int)(C / 4),
-          (__half*)hi, (__half*)lo);
+          (__half*)hi, (__half*)lo, (long long)(ln_bstride / 4));
     QB_LAUNCH_END();
   }
   const int warps = 8;
@@ -453,7 +468,74 @@ extern "C" int qb_dwconv7_ln(const float* x, const float* dw_w, const float* dw_
   }
   const long long total = B * T;
   dwconv7_ln_kernel<<<(unsigned)ceil_div(total, warps), warps * 32, smem, (cudaStream_t)stream>>>(
-      x, dw_w, dw_b, ln_w, ln_b, (int)T, (int)C, total, (__half*)hi, (__half*)lo);
+      x, dw_w, dw_b, ln_w, ln_b, (int)T, (int)C, total, (__half*)hi, (__half*)lo, (long long)ln_bstride);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_dwconv7_ln(const float* x, const float* dw_w, const float* dw_b, const float* ln_w,
+                             const float* ln_b, int64_t B, int64_t T, int64_t C, qb_half* hi, qb_half* lo,
+                             void* stream) {
+  return dwconv7_ln_launch(x, dw_w, dw_b, ln_w, ln_b, 0, B, T, C, hi, lo, stream);
+}
+
+extern "C" int qb_dwconv7_adaln(const float* x, const float* dw_w, const float* dw_b, const float* scale,
+                                const float* shift, int64_t cond_stride, int64_t B, int64_t T, int64_t C, qb_half* hi,
+                                qb_half* lo, void* stream) {
+  return dwconv7_ln_launch(x, dw_w, dw_b, scale, shift, cond_stride, B, T, C, hi, lo, stream);
+}
+
+// ------------------------------------------------------------------ BiCodec WaveGenerator glue
+// Snake (bicodec/modules/blocks/layers.py:33-38): x + sin(alpha x)^2 / (alpha + 1e-9), per channel, written as fp16 planes
+// into the interior of the next convolution's zero-padded channel-last buffer.  x rows of clip b start at
+// x + b * x_bstride (the transposed-conv GEMM leaves its output as a strided view).
+__global__ void snake_planes_kernel(const float* __restrict__ x, long long x_bstride, const float* __restrict__ alpha,
+                                    int T, int C, __half* __restrict__ hi, __half* __restrict__ lo, long long ld,
+                                    long long rpb, long long off, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % ld);
+  const long long r = i / ld;
+  const int t = (int)(r % T);
+  const long long b = r / T;
+  float v = 0.f;
+  if (c < C) {
+    const float xv = x[b * x_bstride + (long long)t * C + c], a = alpha[c];
+    const float sn = sinf(a * xv);
+    v = xv + sn * sn / (a + 1e-9f);
+  }
+  store_planes(hi, lo, (b * rpb + off + t) * ld + c, v);
+}
+
+// x[b, t, c] + vec[b, c] -> planes (the speaker d-vector added to every frame, bicodec/bicodec.py:197)
+__global__ void addvec_planes_kernel(const float* __restrict__ x, const float* __restrict__ vec, int T, int C,
+                                     __half* __restrict__ hi, __half* __restrict__ lo, long long ld, long long rpb,
+                                     long long off, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % ld);
+  const long long r = i / ld;
+  const int t = (int)(r % T);
+  const long long b = r / T;
+  const float v = c < C ? x[(b * T + t) * C + c] + vec[b * C + c] : 0.f;
+  store_planes(hi, lo, (b * rpb + off + t) * ld + c, v);
+}
+
+extern "C" int qb_snake_planes(const float* x, int64_t x_batch_stride, const float* alpha, int64_t B, int64_t T, int64_t C,
+                               qb_half* hi, qb_half* lo, int64_t ld, int64_t rows_per_batch, int64_t row_off,
+                               void* stream) {
+  QB_REQUIRE(x && alpha && hi && C <= ld && row_off + T <= rows_per_batch, "snake_planes: bad args");
+  const long long total = B * T * ld;
+  snake_planes_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, x_batch_stride, alpha, (int)T, (int)C, (__half*)hi, (__half*)lo, ld, rows_per_batch, row_off, total);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_addvec_planes(const float* x, const float* vec, int64_t B, int64_t T, int64_t C, qb_half* hi, qb_half* lo,
+                                int64_t ld, int64_t rows_per_batch, int64_t row_off, void* stream) {
+  QB_REQUIRE(x && vec && hi && C <= ld && row_off + T <= rows_per_batch, "addvec_planes: bad args");
+  const long long total = B * T * ld;
+  addvec_planes_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, vec, (int)T, (int)C, (__half*)hi, (__half*)lo, ld, rows_per_batch, row_off, total);
   QB_LAUNCH_END();
 }
 

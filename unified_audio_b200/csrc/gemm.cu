@@ -38,7 +38,7 @@ struct RowMapD {
 };
 struct GemmParams {
   int tiles_per_batch, num_n_tiles, num_tiles, num_kb;
-  int taps, stride, cblocks, C;
+  int taps, stride, cblocks, C, dil;
   int m_per_batch, N;
   const float* bias;
   const float* gamma;
@@ -53,6 +53,7 @@ struct GemmParams {
 __device__ __forceinline__ float apply_act(int act, float v) {
   if (act == QB_ACT_GELU) return gelu_fast(v);
   if (act == QB_ACT_ELU) return elu_f(v);
+  if (act == QB_ACT_TANH) return tanhf(v);
   return v;
 }
 
@@ -265,7 +266,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* s = smem + stage * STAGE_BYTES;
-          const int ax = (tap % p.stride) * p.C + cb * BK, ay = m0 + tap / p.stride, wx = tap * p.C + cb * BK;
+          const int tt = tap * p.dil;      // input row of output row m: m * stride + tap * dilation
+          const int ax = (tt % p.stride) * p.C + cb * BK, ay = m0 + tt / p.stride, wx = tap * p.C + cb * BK;
           tma_load_3d(s, &tmA_hi, &full[stage], ax, ay, b);
           if (NPL == 2) tma_load_3d(s + A_BYTES, &tmA_lo, &full[stage], ax, ay, b);
           tma_load_2d(s + NPL * A_BYTES, &tmW_hi, &full[stage], wx, n0);
@@ -396,7 +398,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
           const uint32_t fb = mapa_u32(smem_u32(&full[stage]), 0);
           uint8_t* s = smem + stage * STAGE_BYTES;
-          const int ax = (tap % p.stride) * p.C + cb * BK, ay = m0 + tap / p.stride, wx = tap * p.C + cb * BK;
+          const int tt = tap * p.dil;      // input row of output row m: m * stride + tap * dilation
+          const int ax = (tt % p.stride) * p.C + cb * BK, ay = m0 + tt / p.stride, wx = tap * p.C + cb * BK;
           tma2_load_3d(s, &tmA_hi, fb, ax, ay, b);
           if (NPL == 2) tma2_load_3d(s + A_BYTES, &tmA_lo, fb, ax, ay, b);
           tma2_load_2d(s + NPL * A_BYTES, &tmW_hi, fb, wx, n0);
@@ -481,7 +484,7 @@ __global__ void gemm_simt_kernel(const GemmParams p) {
   auto dot = [&](int col) {
     float acc = 0.f;
     for (int t = 0; t < p.taps; ++t) {
-      long long row = (long long)m * p.stride + t;
+      long long row = (long long)m * p.stride + (long long)t * p.dil;
       if (row >= p.a_rpb) continue;
       const __half* ah = p.a_hi + ((long long)b * p.a_rpb + row) * p.C;
       const __half* al = p.a_lo ? p.a_lo + ((long long)b * p.a_rpb + row) * p.C : nullptr;
@@ -556,6 +559,7 @@ static int fill_params(const qb_gemm_desc* d, GemmParams* p, int BN) {
   p->num_n_tiles = (int)ceil_div(d->n, BN);
   p->num_tiles = (int)(d->a_batch * p->tiles_per_batch * p->num_n_tiles);
   p->taps = d->taps; p->stride = d->stride; p->C = (int)d->a_ld; p->cblocks = (int)(d->a_ld / 64);
+  p->dil = d->dilation > 0 ? d->dilation : 1;
   p->num_kb = p->taps * p->cblocks;
   p->m_per_batch = (int)d->m_per_batch; p->N = (int)d->n;
   p->bias = d->bias; p->gamma = d->gamma;

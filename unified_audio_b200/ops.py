@@ -9,7 +9,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ACT_ELU, ACT_GELU, ACT_NONE, ACT_SWIGLU, GemmDesc, RowMap  # noqa: F401
+from ._lib import ACT_ELU, ACT_GELU, ACT_NONE, ACT_SWIGLU, ACT_TANH, GemmDesc, RowMap  # noqa: F401
 
 
 def _stream():
@@ -53,13 +53,13 @@ def rowmap(t: Optional[torch.Tensor], ld=0, rows_per_batch=0, row_off=0) -> RowM
 def gemm(a: Planes, w: Planes, n: int, *, a_batch: int, a_rows_per_batch: int, a_ld: int, m_per_batch: int,
          taps: int = 1, stride: int = 1, bias=None, gamma=None, residual: Optional[RowMap] = None, act=ACT_NONE,
          act2=ACT_NONE, out_f32: Optional[RowMap] = None, out_planes: Optional[Planes] = None,
-         out_planes_map=(0, 0, 0), simt: bool = False):
+         out_planes_map=(0, 0, 0), simt: bool = False, dilation: int = 1):
     """One dense contraction (see qb_gemm_desc).  Split mode iff both a.lo and w.lo are given."""
     split = a.lo is not None and w.lo is not None
     d = GemmDesc()
     d.a_hi, d.a_lo = _p(a.hi), (_p(a.lo) if split else None)
     d.a_batch, d.a_rows_per_batch, d.a_ld = a_batch, a_rows_per_batch, a_ld
-    d.taps, d.stride, d.m_per_batch = taps, stride, m_per_batch
+    d.taps, d.stride, d.m_per_batch, d.dilation = taps, stride, m_per_batch, dilation
     d.w_hi, d.w_lo, d.n = _p(w.hi), (_p(w.lo) if split else None), n
     d.bias, d.gamma = _p(bias), _p(gamma)
     d.residual = residual if residual is not None else RowMap(None, 0, 0, 0)
@@ -110,6 +110,31 @@ def rmsnorm(x, w, rows, Cc, out: Optional[Planes] = None, eps=1e-6, out_f32=None
 def dwconv7_ln(x, dw_w, dw_b, ln_w, ln_b, B, T, Cc, out: Planes):
     _lib.check(_lib.load().qb_dwconv7_ln(_p(x), _p(dw_w), _p(dw_b), _p(ln_w), _p(ln_b), B, T, Cc, _p(out.hi), _p(out.lo),
                                          _stream()))
+
+
+def dwconv7_adaln(x, dw_w, dw_b, scale, shift, cond_stride, B, T, Cc, out: Planes):
+    _lib.check(_lib.load().qb_dwconv7_adaln(_p(x), _p(dw_w), _p(dw_b), _p(scale), _p(shift), cond_stride, B, T, Cc, _p(out.hi),
+                                            _p(out.lo), _stream()))
+
+
+def adalayernorm(x, scale, shift, cond_stride, B, rows, Cc, eps=1e-6, out_f32=None, out: Optional[Planes] = None, ld=0,
+                 rows_per_batch=0, row_off=0):
+    hi = out.hi if out is not None else None
+    lo = out.lo if out is not None else None
+    if out is not None and ld == 0:
+        ld, rows_per_batch, row_off = Cc, rows, 0
+    _lib.check(_lib.load().qb_adalayernorm(_p(x), _p(scale), _p(shift), cond_stride, eps, B, rows, Cc, _p(out_f32), _p(hi),
+                                           _p(lo), ld, rows_per_batch, row_off, _stream()))
+
+
+def snake_planes(x, x_batch_stride, alpha, B, T, Cc, out: Planes, ld, rows_per_batch, row_off):
+    _lib.check(_lib.load().qb_snake_planes(_p(x), x_batch_stride, _p(alpha), B, T, Cc, _p(out.hi), _p(out.lo), ld,
+                                           rows_per_batch, row_off, _stream()))
+
+
+def addvec_planes(x, vec, B, T, Cc, out: Planes, ld, rows_per_batch, row_off):
+    _lib.check(_lib.load().qb_addvec_planes(_p(x), _p(vec), B, T, Cc, _p(out.hi), _p(out.lo), ld, rows_per_batch, row_off,
+                                            _stream()))
 
 
 def groupnorm_stats(x, B, T, Cc, stats, groups=32, eps=1e-6):
