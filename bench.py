@@ -308,6 +308,155 @@ def run_lm(args):
         dist.destroy_process_group()
 
 
+def bicodec_flops_per_clip(cfg, T):
+    """algorithmic FLOPs of BiCodec.detokenize for one clip of T tokens (2 x MACs, true channel counts and taps)"""
+    p, d = cfg["prenet"], cfg["decoder"]
+    dim, inter = p["vocos_dim"], p["vocos_intermediate_dim"]
+    blocks = 2 * len(p["sample_ratios"]) + p["vocos_num_layers"]
+    backbones = len(p["sample_ratios"]) + 1
+    f = 2.0 * T * (p["input_channels"] * dim + backbones * dim * dim * 7 + blocks * 2 * dim * inter + dim * p["out_channels"])
+    ch = d["channels"]
+    f += 2.0 * T * d["input_channel"] * ch * 7
+    Tc = T
+    for i, (k, r) in enumerate(zip(d["kernel_sizes"], d["rates"])):
+        cin, cout = ch // 2 ** i, ch // 2 ** (i + 1)
+        f += 2.0 * Tc * cin * cout * k                     # transposed conv: k taps per INPUT frame
+        Tc *= r
+        f += 3 * 2.0 * Tc * cout * cout * 8                # 3 residual units: dilated k7 + 1x1
+    f += 2.0 * Tc * (ch // 2 ** len(d["rates"])) * 7
+    return f
+
+
+def run_bicodec(args):
+    """Secondary line: BiCodec.detokenize, the decoder UniSE feeds its AR-LM tokens to (configs[2] back half):
+    B=32 clips x 250 semantic tokens + 32 global tokens -> 5 s @ 16 kHz each."""
+    B, T = 32, 250
+    if args.impl == "reference":
+        from oracle import bicodec as ob
+        cfg = ob.BICODEC_FULL
+        sd = ob.make_state_dict(cfg, 5)
+        sem, glob = ob.synth_tokens(cfg, 1, T, 9)
+        torch.set_num_threads(min(16, os.cpu_count() or 1))
+        ob.detokenize(sd, cfg, sem[:, :25], glob)
+        t0 = time.perf_counter()
+        ob.detokenize(sd, cfg, sem, glob)
+        dt = time.perf_counter() - t0
+        v = T * 320 / dt
+        print(json.dumps(dict(metric="bicodec_detokenize_samples_per_s", value=v, unit="samples/s", n_gpus=args.gpus, steps=1,
+                              warmup=1, ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                              dtype="f32", data="synthetic", impl="reference",
+                              config=dict(workload="BiCodec detokenize, 1 clip x 250 tokens -> 5 s @ 16 kHz", batch=1),
+                              cpu_baseline=dict(value=v, unit="samples/s", cores=torch.get_num_threads(), kind="port",
+                                                sample="1 clip x 5 s, oracle port pinned against the reference's BiCodec classes"),
+                              e2e=dict(value=v, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)))
+        return
+    from unified_audio_b200 import ops
+    from unified_audio_b200.bicodec import BICODEC_CONFIG, BiCodec
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:       # clips are independent: B per rank, no data-path collective (the waveforms stay on their rank)
+        import torch.distributed as dist_
+        dist = dist_
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = BICODEC_CONFIG
+    m = BiCodec(cfg).to(dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith("alpha"):
+                p.copy_(1 + 0.3 * torch.rand(p.shape, generator=g, device=dev))
+            elif n.endswith(("weight_g",)):
+                p.fill_(1.0)
+            elif p.dim() >= 2:
+                fan = p[0].numel() if "block.1.weight_v" not in n else 2 * p.shape[0]
+                p.copy_(torch.randn(p.shape, generator=g, device=dev) / fan ** 0.5)
+            elif n.endswith(("gamma",)):
+                p.fill_(1.0 / 12)
+            elif n.endswith(("norm.weight", "scale.bias", "final_layer_norm.weight")):
+                p.fill_(1.0)
+            else:
+                p.copy_(0.02 * torch.randn(p.shape, generator=g, device=dev))
+        sdm = m.state_dict()
+        for n in list(sdm):     # weight-norm gains ~ ||v||, residual branches damped (as oracle.bicodec.make_state_dict)
+            if n.endswith("weight_g"):
+                v = sdm[n[:-1] + "v"]
+                gain = 0.3 if ".block.3." in n else (0.1 if n.startswith("decoder.model.6.") else 1.0)
+                sdm[n].copy_(gain * v.reshape(v.shape[0], -1).norm(dim=1).reshape(sdm[n].shape))
+    m._w = None
+    gt = torch.Generator().manual_seed(50 + rank)
+    sem_h = torch.randint(0, cfg["quantizer"]["codebook_size"], (B, T), generator=gt).pin_memory()
+    glob_h = torch.randint(0, 4096, (B, 1, 32), generator=gt).pin_memory()
+    sem, glob = sem_h.to(dev), glob_h.to(dev)
+    wav_h = torch.empty(B, 1, T * 320).pin_memory()
+
+    def timed(fn):
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    for _ in range(max(args.warmup, 3)):
+        m.detokenize(sem, glob)
+    if args.quick:
+        ms = timed(lambda: m.detokenize(sem, glob))
+        if rank == 0:
+            print(json.dumps(dict(quick=True, ms_per_step=ms)))
+        return
+    ops.launch_count_reset()
+    ms = timed(lambda: m.detokenize(sem, glob))
+    launches = ops.launch_count()
+
+    def e2e_step():
+        w = m.detokenize(sem_h.to(dev, non_blocking=True), glob_h.to(dev, non_blocking=True))
+        wav_h.copy_(w, non_blocking=True)
+    ms_e2e = timed(e2e_step)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    samples = world * B * T * 320
+    tf = world * B * bicodec_flops_per_clip(cfg, T) / (ms * 1e-3) / 1e12
+    cpu = None
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "bicodec", "--impl", "reference"],
+                           capture_output=True, text=True, timeout=600)
+        cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+    except Exception as e:      # the baseline is reported, never required for the GPU line
+        cpu = dict(value=None, unit="samples/s", cores=0, kind="port", sample=f"failed: {e}")
+    print(json.dumps(dict(
+        metric="bicodec_detokenize_samples_per_s", value=samples / (ms * 1e-3), unit="samples/s", n_gpus=world, steps=args.steps,
+        warmup=max(args.warmup, 3), ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype="f16x3 split tensor-core (fp32-grade), f32 accumulate", data="synthetic",
+        config=dict(workload="BiCodec detokenize (UniSE's decoder): 32 clips x 250 semantic + 32 global tokens -> 5 s @ 16 kHz",
+                    batch_per_gpu=B, tokens=T, precision_policy="accurate",
+                    l2="activations per step (~10 GB) exceed the 126 MB L2; no flush needed",
+                    parallelism=f"dp{world} (clips sharded, no collective)"),
+        e2e=dict(value=samples / (ms_e2e * 1e-3), unit="samples/s", ms_per_step=ms_e2e,
+                 h2d_bytes_per_step=int(sem_h.numel() * 8 + glob_h.numel() * 8) * world,
+                 d2h_bytes_per_step=int(wav_h.numel() * 4) * world),
+        gpu_launches=int(launches),
+        roofline=dict(bound="tensor", achieved=tf, peak=peaks["tf_sus"] * world, unit="TFLOP/s", frac=tf / (peaks["tf_sus"] * world),
+                      traffic=None, kernel="whole detokenize path, algorithmic FLOPs (true channels / taps; every GEMM issued 3x in the "
+                      "`accurate` policy) against the sustained bf16 peak"),
+        cpu_baseline=cpu)))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -320,14 +469,17 @@ def main():
     ap.add_argument("--precision", default="mixed")
     ap.add_argument("--ref-clips", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="codec", choices=["codec", "lm"],
-                    help="codec = BASELINE configs[1] (default, the driver's line); lm = UniSE SR AR-LM generate (configs[2])")
+    ap.add_argument("--workload", default="codec", choices=["codec", "lm", "bicodec"],
+                    help="codec = BASELINE configs[1] (default, the driver's line); lm = UniSE SR AR-LM generate (configs[2]); "
+                         "bicodec = BiCodec detokenize, the decoder UniSE feeds the LM tokens to")
     ap.add_argument("--quick", action="store_true", help="profiling aid: W warm-up + K steps only, no e2e/roofline/cpu legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     cfg = H2_FULL
     if args.workload == "lm":
         return run_lm(args)
+    if args.workload == "bicodec":
+        return run_bicodec(args)
     if args.impl == "reference":
         return run_reference(args, cfg)
 

@@ -40,7 +40,7 @@ int64_t qb_launch_count(void);
 void qb_launch_count_reset(void);
 
 /* activation codes for the GEMM epilogue */
-enum { QB_ACT_NONE = 0, QB_ACT_GELU = 1, QB_ACT_SWIGLU = 2, QB_ACT_ELU = 3, QB_ACT_TANH = 4 };
+enum { QB_ACT_NONE = 0, QB_ACT_GELU = 1, QB_ACT_SWIGLU = 2, QB_ACT_ELU = 3, QB_ACT_TANH = 4, QB_ACT_SNAKE = 5 };
 
 /* Row mapping of an output / residual tensor: GEMM row (batch b, row m) lives at
  * ptr + ((b * rows_per_batch + row_off + m) * ld + n).  Lets a GEMM write straight into the
@@ -79,12 +79,15 @@ typedef struct {
   const float* gamma;       /* [n] or NULL */
   qb_rowmap residual;       /* fp32, ptr NULL => none */
   int32_t act;              /* QB_ACT_* applied to v before gamma/residual */
-  int32_t act2;             /* QB_ACT_NONE or QB_ACT_ELU, applied only to the fp16-plane output */
+  int32_t act2;             /* QB_ACT_NONE, QB_ACT_ELU or QB_ACT_SNAKE, applied only to the fp16-plane output */
   qb_rowmap out_f32;        /* ptr NULL => not written */
   qb_rowmap out_hi;         /* fp16 planes; ptr NULL => not written */
   qb_rowmap out_lo;         /* ptr NULL => hi only (same ld / mapping fields as out_hi required) */
   int32_t dilation;         /* tap spacing in input rows: A[b, m*stride + tap*dilation, c]; 0 or 1 = dense taps.
                              * (DAC residual units, bicodec/modules/blocks/layers.py:52-60: k=7, dilation 1/3/9) */
+  const float* act_param;   /* [n] per-column parameter of `act`  (QB_ACT_SNAKE: alpha) or NULL */
+  const float* act2_param;  /* [n] per-column parameter of `act2` (QB_ACT_SNAKE on the plane output only: the fp32 output is
+                             * the residual trunk, the planes are Snake(trunk) for the next convolution) or NULL */
 } qb_gemm_desc;
 
 /* tcgen05 / TMA / TMEM persistent GEMM (the product path). */

@@ -171,7 +171,8 @@ def test_gemm_desc_struct_layout_matches_header():
     assert C.sizeof(RowMap) == 32
     assert GemmDesc.taps.offset == 40 and GemmDesc.stride.offset == 44 and GemmDesc.m_per_batch.offset == 48
     assert GemmDesc.residual.offset == 96 and GemmDesc.act.offset == 128 and GemmDesc.out_f32.offset == 136
-    assert GemmDesc.dilation.offset == 136 + 3 * 32 and C.sizeof(GemmDesc) == 136 + 3 * 32 + 8
+    assert GemmDesc.dilation.offset == 136 + 3 * 32 and GemmDesc.act_param.offset == 136 + 3 * 32 + 8
+    assert C.sizeof(GemmDesc) == 136 + 3 * 32 + 24
 
 
 def test_bench_reference_arm_contract():

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libquark_b200.so")
 
-ACT_NONE, ACT_GELU, ACT_SWIGLU, ACT_ELU, ACT_TANH = 0, 1, 2, 3, 4
+ACT_NONE, ACT_GELU, ACT_SWIGLU, ACT_ELU, ACT_TANH, ACT_SNAKE = 0, 1, 2, 3, 4, 5
 
 
 class RowMap(C.Structure):
@@ -24,7 +24,7 @@ class GemmDesc(C.Structure):
         ("a_ld", C.c_int64), ("taps", C.c_int32), ("stride", C.c_int32), ("m_per_batch", C.c_int64),
         ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("n", C.c_int64), ("bias", C.c_void_p), ("gamma", C.c_void_p),
         ("residual", RowMap), ("act", C.c_int32), ("act2", C.c_int32), ("out_f32", RowMap), ("out_hi", RowMap),
-        ("out_lo", RowMap), ("dilation", C.c_int32),
+        ("out_lo", RowMap), ("dilation", C.c_int32), ("act_param", C.c_void_p), ("act2_param", C.c_void_p),
     ]
 
 

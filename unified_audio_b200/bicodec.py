@@ -27,7 +27,7 @@ from torch import nn
 
 from . import ops
 from .codec import _Tree, _pad_to
-from .ops import ACT_GELU, ACT_NONE, ACT_TANH, Planes, rowmap
+from .ops import ACT_GELU, ACT_SNAKE, ACT_TANH, Planes, rowmap
 
 BICODEC_CONFIG = dict(
     sample_rate=16000, hop=320,
@@ -355,54 +355,75 @@ class BiCodec(nn.Module):
         if p["use_tanh_at_final"]:
             raise NotImplementedError("prenet use_tanh_at_final (False in the shipped configuration)")
         # ---- WaveGenerator (wave_generator.py:59-91)
+        # Every Snake but one per stage rides in a GEMM epilogue: a conv's fp32 output is the residual trunk, its fp16-plane
+        # output is Snake_alpha(trunk) written straight into the interior of the NEXT convolution's zero-padded buffer
+        # (qb_gemm_desc.act2 / act2_param); the dilated conv's own Snake is `act`.  Only the transposed conv's output - all
+        # s phases of a frame in one row, shifted by the padding - needs the stand-alone Snake kernel.
         G = W["gen"]
         a0 = self._planes("gen_in", (B, T + 6, C0), sp_gen)
         ops.addvec_planes(pre, dvec, B, T, C0, a0, C0, T + 6, 3)                    # x + d_vector[:, :, None]  (bicodec.py:197)
         ch = d["channels"]
-        trunk = self._buf("gen_t0", (M, ch))
-        self._conv(a0, G["conv0"], ch, B, T + 6, C0, T, 7, bias=G["conv0_b"], out_f32=rowmap(trunk, ch, T, 0))
+        stages = G["stages"]
+
+        def up_in(si, Tc):      # padded input buffer of stage si's transposed conv
+            st = stages[si]
+            cpi = _pad_to(st["cin"], 64)
+            return self._planes(f"gen_up_in{si}", (B, Tc + 2 * (st["J"] - 1), cpi), sp_gen), cpi, Tc + 2 * (st["J"] - 1), st["J"] - 1
+
+        Tc = T
+        nxt_pl, nxt_ld, nxt_rpb, nxt_off = up_in(0, Tc)
+        self._conv(a0, G["conv0"], ch, B, T + 6, C0, T, 7, bias=G["conv0_b"], act2=ACT_SNAKE, act2_param=stages[0]["alpha"],
+                   out_planes=nxt_pl, out_planes_map=(nxt_ld, nxt_rpb, nxt_off))
         if taps is not None:
             taps["z_q"], taps["d_vector"], taps["prenet.out"] = zq.clone(), dvec.clone(), pre.clone()
-        Tc = T
-        t_base, t_bstride, t_rpb, t_off = trunk, Tc * ch, Tc, 0                     # fp32 trunk: pointer, clip stride, row map
-        for si, st in enumerate(G["stages"]):
+        cl = ch // 2 ** len(d["rates"])
+        for si, st in enumerate(stages):
             cin, cout, J, sdn, k = st["cin"], st["cout"], st["J"], st["s"], st["k"]
-            cpi, cpo = _pad_to(cin, 64), _pad_to(cout, 64)
-            # Snake -> transposed conv as a J-tap GEMM producing all `s` phases of every input frame
-            a = self._planes(f"gen_up_in{si}", (B, Tc + 2 * (J - 1), cpi), sp_gen)
-            ops.snake_planes(t_base, t_bstride, st["alpha"], B, Tc, cin, a, cpi, Tc + 2 * (J - 1), J - 1)
+            cpo = _pad_to(cout, 64)
+            a, cpi, rows_in, _ = up_in(si, Tc)
+            # transposed conv as a J-tap GEMM producing all `s` phases of every input frame
             up = self._buf(f"gen_up{si}", (B, Tc + J - 1, sdn * cout))
-            self._conv(a, st["wt"], sdn * cout, B, Tc + 2 * (J - 1), cpi, Tc + J - 1, J, bias=st["bt"],
+            self._conv(a, st["wt"], sdn * cout, B, rows_in, cpi, Tc + J - 1, J, bias=st["bt"],
                        out_f32=rowmap(up, sdn * cout, Tc + J - 1, 0))
             pad_t = (k - sdn) // 2
             Tn = Tc * sdn
             # the up-sampled clip b is rows [pad_t, pad_t + Tn) of up[b] viewed as [(Tc + J - 1) * s, cout]
-            t_base = up.view(-1)[pad_t * cout:]
-            t_bstride, t_rpb, t_off = (Tc + J - 1) * sdn * cout, (Tc + J - 1) * sdn, pad_t
-            res_ptr = up
+            res = rowmap(up, cout, (Tc + J - 1) * sdn, pad_t)
+            units = st["units"]
+            bufs = [self._planes(f"gen_u{si}_{u['dil']}", (B, Tn + 6 * u["dil"], cpo), sp_gen) for u in units]
+            ops.snake_planes(up.view(-1)[pad_t * cout:], (Tc + J - 1) * sdn * cout, units[0]["a1"], B, Tn, cout, bufs[0], cpo,
+                             Tn + 6 * units[0]["dil"], 3 * units[0]["dil"])
+            a2 = self._planes(f"gen_v{si}", (B * Tn, cpo), sp_gen)
             dense = [self._buf(f"gen_x{si}a", (B * Tn, cout)), self._buf(f"gen_x{si}b", (B * Tn, cout))]
-            y = self._buf(f"gen_y{si}", (B * Tn, cout))
-            for ui, un in enumerate(st["units"]):
+            for ui, un in enumerate(units):
                 dil = un["dil"]
-                a1 = self._planes(f"gen_u{si}_{dil}", (B, Tn + 6 * dil, cpo), sp_gen)
-                ops.snake_planes(t_base, t_bstride, un["a1"], B, Tn, cout, a1, cpo, Tn + 6 * dil, 3 * dil)
-                self._conv(a1, un["w1"], cout, B, Tn + 6 * dil, cpo, Tn, 7, dilation=dil, bias=un["b1"],
-                           out_f32=rowmap(y, cout, Tn, 0))
-                a2 = self._planes(f"gen_v{si}", (B * Tn, cpo), sp_gen)
-                ops.snake_planes(y, Tn * cout, un["a2"], B, Tn, cout, a2, cpo, Tn, 0)
+                # Snake -> dilated k7 conv -> Snake (epilogue) -> planes
+                self._conv(bufs[ui], un["w1"], cout, B, Tn + 6 * dil, cpo, Tn, 7, dilation=dil, bias=un["b1"], act=ACT_SNAKE,
+                           act_param=un["a2"], out_planes=a2, out_planes_map=(cpo, Tn, 0))
+                # 1x1 conv + residual -> fp32 trunk, and Snake(trunk) planes for whoever consumes it next
+                last = ui == len(units) - 1
+                if not last:
+                    nd = units[ui + 1]["dil"]
+                    n_pl, n_ld, n_rpb, n_off, n_alpha = bufs[ui + 1], cpo, Tn + 6 * nd, 3 * nd, units[ui + 1]["a1"]
+                elif si + 1 < len(stages):
+                    n_pl, n_ld, n_rpb, n_off = up_in(si + 1, Tn)
+                    n_alpha = stages[si + 1]["alpha"]
+                else:
+                    cpf = _pad_to(cl, 64)
+                    n_pl, n_ld, n_rpb, n_off, n_alpha = self._planes("gen_f", (B, Tn + 6, cpf), sp_gen), cpf, Tn + 6, 3, G["alpha_f"]
                 nxt = dense[ui & 1]
-                ops.gemm(a2, un["w2"], cout, a_batch=B, a_rows_per_batch=Tn, a_ld=cpo, m_per_batch=Tn, bias=un["b2"],
-                         residual=rowmap(res_ptr, cout, t_rpb, t_off), out_f32=rowmap(nxt, cout, Tn, 0))
-                t_base, t_bstride, t_rpb, t_off, res_ptr = nxt, Tn * cout, Tn, 0, nxt
+                need_f32 = (not last) or taps is not None
+                ops.gemm(a2, un["w2"], cout, a_batch=B, a_rows_per_batch=Tn, a_ld=cpo, m_per_batch=Tn, bias=un["b2"], residual=res,
+                         out_f32=rowmap(nxt, cout, Tn, 0) if need_f32 else None, act2=ACT_SNAKE, act2_param=n_alpha,
+                         out_planes=n_pl, out_planes_map=(n_ld, n_rpb, n_off))
+                res = rowmap(nxt, cout, Tn, 0)
             Tc = Tn
             if taps is not None:
-                taps[f"dec.stage{si}"] = t_base.clone().reshape(B, Tc, cout)
-        cl = d["channels"] // 2 ** len(d["rates"])
-        cpl_ = _pad_to(cl, 64)
-        af = self._planes("gen_f", (B, Tc + 6, cpl_), sp_gen)
-        ops.snake_planes(t_base, t_bstride, G["alpha_f"], B, Tc, cl, af, cpl_, Tc + 6, 3)
+                taps[f"dec.stage{si}"] = dense[(len(units) - 1) & 1].clone().reshape(B, Tc, cout)
+        cpf = _pad_to(cl, 64)
+        af = self._planes("gen_f", (B, Tc + 6, cpf), sp_gen)
         wav = torch.empty(B, 1, Tc, device=dev)
-        self._conv(af, G["conv_f"], 1, B, Tc + 6, cpl_, Tc, 7, bias=G["conv_f_b"], act=ACT_TANH, out_f32=rowmap(wav, 1, Tc, 0))
+        self._conv(af, G["conv_f"], 1, B, Tc + 6, cpf, Tc, 7, bias=G["conv_f_b"], act=ACT_TANH, out_f32=rowmap(wav, 1, Tc, 0))
         return wav
 
     def forward(self, *a, **k):

@@ -488,6 +488,46 @@ extern "C" int qb_dwconv7_adaln(const float* x, const float* dw_w, const float* 
 // Snake (bicodec/modules/blocks/layers.py:33-38): x + sin(alpha x)^2 / (alpha + 1e-9), per channel, written as fp16 planes
 // into the interior of the next convolution's zero-padded channel-last buffer.  x rows of clip b start at
 // x + b * x_bstride (the transposed-conv GEMM leaves its output as a strided view).
+// 8 channels per thread: two 16-byte loads, one 16-byte store per plane
+__global__ void snake_planes_v8_kernel(const float* __restrict__ x, long long x_bstride, const float* __restrict__ alpha,
+                                       int T, int C8, int ld8, __half* __restrict__ hi, __half* __restrict__ lo,
+                                       long long rpb, long long off, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % ld8);
+  const long long r = i / ld8;
+  const int t = (int)(r % T);
+  const long long b = r / T;
+  float v[8];
+  if (c8 < C8) {
+    const float4* xp = reinterpret_cast<const float4*>(x + b * x_bstride + ((long long)t * C8 + c8) * 8);
+    const float4* ap = reinterpret_cast<const float4*>(alpha + c8 * 8);
+    const float4 x0 = xp[0], x1 = xp[1], a0 = __ldg(ap), a1 = __ldg(ap + 1);
+    const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    const float as[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float sn = sinf(as[e] * xs[e]);
+      v[e] = fmaf(1.0f / (as[e] + 1e-9f), sn * sn, xs[e]);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  }
+  __half2 h2[4], l2[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __half a, bq, la, lb;
+    split_f16(v[2 * e], a, la);
+    split_f16(v[2 * e + 1], bq, lb);
+    h2[e] = __halves2half2(a, bq);
+    l2[e] = __halves2half2(la, lb);
+  }
+  const long long o = ((b * rpb + off + t) * ld8 + c8);
+  reinterpret_cast<uint4*>(hi)[o] = *reinterpret_cast<uint4*>(h2);
+  if (lo) reinterpret_cast<uint4*>(lo)[o] = *reinterpret_cast<uint4*>(l2);
+}
+
 __global__ void snake_planes_kernel(const float* __restrict__ x, long long x_bstride, const float* __restrict__ alpha,
                                     int T, int C, __half* __restrict__ hi, __half* __restrict__ lo, long long ld,
                                     long long rpb, long long off, long long total) {
@@ -525,6 +565,13 @@ extern "C" int qb_snake_planes(const float* x, int64_t x_batch_stride, const flo
                                void* stream) {
   QB_REQUIRE(x && alpha && hi && C <= ld && row_off + T <= rows_per_batch, "snake_planes: bad args");
   const long long total = B * T * ld;
+  if (C % 8 == 0 && ld % 8 == 0 && x_batch_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(alpha) & 15) == 0) {
+    snake_planes_v8_kernel<<<(unsigned)ceil_div(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, x_batch_stride, alpha, (int)T, (int)(C / 8), (int)(ld / 8), (__half*)hi, (__half*)lo, rows_per_batch, row_off,
+        total / 8);
+    QB_LAUNCH_END();
+  }
   snake_planes_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
       x, x_batch_stride, alpha, (int)T, (int)C, (__half*)hi, (__half*)lo, ld, rows_per_batch, row_off, total);
   QB_LAUNCH_END();

@@ -42,6 +42,8 @@ struct GemmParams {
   int m_per_batch, N;
   const float* bias;
   const float* gamma;
+  const float* act_p;    // per-column parameter of `act` (Snake alpha)
+  const float* act2_p;   // per-column parameter of `act2`
   RowMapD res, o32, ohi, olo;
   int act, act2;
   // SIMT path only
@@ -50,6 +52,11 @@ struct GemmParams {
   int a_batch;
 };
 
+// Snake (bicodec/modules/blocks/layers.py:33-38): x + (alpha + 1e-9)^-1 * sin(alpha x)^2
+__device__ __forceinline__ float snake_f(float v, float a) {
+  const float sn = sinf(a * v);
+  return fmaf(1.0f / (a + 1e-9f), sn * sn, v);
+}
 __device__ __forceinline__ float apply_act(int act, float v) {
   if (act == QB_ACT_GELU) return gelu_fast(v);
   if (act == QB_ACT_ELU) return elu_f(v);
@@ -63,7 +70,7 @@ __device__ __forceinline__ void epi_finish_scalar(const GemmParams& p, int b, in
   if (p.res.ptr) v += ((const float*)p.res.ptr)[((long long)b * p.res.rpb + p.res.off + m) * p.res.ld + n];
   if (p.o32.ptr) ((float*)p.o32.ptr)[((long long)b * p.o32.rpb + p.o32.off + m) * p.o32.ld + n] = v;
   if (p.ohi.ptr) {
-    float u = p.act2 == QB_ACT_ELU ? elu_f(v) : v;
+    float u = p.act2 == QB_ACT_ELU ? elu_f(v) : (p.act2 == QB_ACT_SNAKE ? snake_f(v, __ldg(p.act2_p + n)) : v);
     __half h, l;
     split_f16(u, h, l);
     long long o = ((long long)b * p.ohi.rpb + p.ohi.off + m) * p.ohi.ld + n;
@@ -144,6 +151,10 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int b, int m
     ncols = 16;
     n_out = n_base >> 1;
     N_out = p.N >> 1;
+  } else if (p.act == QB_ACT_SNAKE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n_base + j < p.N) v[j] = snake_f(v[j], __ldg(p.act_p + n_base + j));
   } else if (p.act != QB_ACT_NONE) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = apply_act(p.act, v[j]);
@@ -200,6 +211,10 @@ __device__ __forceinline__ void epilogue_row32(const GemmParams& p, int b, int m
         for (int e = 0; e < 4; ++e) {
           float u0 = v[8 * j + 2 * e], u1 = v[8 * j + 2 * e + 1];
           if (p.act2 == QB_ACT_ELU) { u0 = elu_f(u0); u1 = elu_f(u1); }
+          if (p.act2 == QB_ACT_SNAKE) {
+            const float2 al = __ldg(reinterpret_cast<const float2*>(p.act2_p + n_out + 8 * j + 2 * e));
+            u0 = snake_f(u0, al.x); u1 = snake_f(u1, al.y);
+          }
           const __half2 hh = __hmax2(__hmin2(__floats2half2_rn(u0, u1), hmax), hmin);   // saturate, no inf
           h2[e] = hh;
           if (lp) {
@@ -509,7 +524,7 @@ __global__ void gemm_simt_kernel(const GemmParams p) {
   } else {
     v = dot(n);
     if (p.bias) v += p.bias[n];
-    v = apply_act(p.act, v);
+    v = p.act == QB_ACT_SNAKE ? snake_f(v, p.act_p[n]) : apply_act(p.act, v);
   }
   epi_finish_scalar(p, b, m, n, v);
 }
@@ -554,6 +569,9 @@ static int fill_params(const qb_gemm_desc* d, GemmParams* p, int BN) {
   QB_REQUIRE(d->a_batch >= 1 && d->m_per_batch >= 1 && d->n >= 1, "gemm: empty problem");
   QB_REQUIRE(d->act != QB_ACT_SWIGLU || d->n % 2 == 0, "gemm: SWIGLU needs even n");
   QB_REQUIRE(!d->out_lo.ptr || d->out_hi.ptr, "gemm: out_lo without out_hi");
+  QB_REQUIRE(d->act != QB_ACT_SNAKE || d->act_param, "gemm: QB_ACT_SNAKE needs act_param (alpha[n])");
+  QB_REQUIRE(d->act2 != QB_ACT_SNAKE || (d->act2_param && (reinterpret_cast<uintptr_t>(d->act2_param) & 7) == 0),
+             "gemm: act2 = QB_ACT_SNAKE needs an 8-byte aligned act2_param (alpha[n])");
   memset(p, 0, sizeof(*p));
   p->tiles_per_batch = (int)ceil_div(d->m_per_batch, 128);
   p->num_n_tiles = (int)ceil_div(d->n, BN);
@@ -562,7 +580,7 @@ static int fill_params(const qb_gemm_desc* d, GemmParams* p, int BN) {
   p->dil = d->dilation > 0 ? d->dilation : 1;
   p->num_kb = p->taps * p->cblocks;
   p->m_per_batch = (int)d->m_per_batch; p->N = (int)d->n;
-  p->bias = d->bias; p->gamma = d->gamma;
+  p->bias = d->bias; p->gamma = d->gamma; p->act_p = d->act_param; p->act2_p = d->act2_param;
   p->res = to_rm(d->residual); p->o32 = to_rm(d->out_f32); p->ohi = to_rm(d->out_hi); p->olo = to_rm(d->out_lo);
   if (p->olo.ptr) { p->olo.ld = p->ohi.ld; p->olo.rpb = p->ohi.rpb; p->olo.off = p->ohi.off; }
   p->act = d->act; p->act2 = d->act2;

@@ -9,7 +9,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ACT_ELU, ACT_GELU, ACT_NONE, ACT_SWIGLU, ACT_TANH, GemmDesc, RowMap  # noqa: F401
+from ._lib import ACT_ELU, ACT_GELU, ACT_NONE, ACT_SNAKE, ACT_SWIGLU, ACT_TANH, GemmDesc, RowMap  # noqa: F401
 
 
 def _stream():
@@ -53,7 +53,7 @@ def rowmap(t: Optional[torch.Tensor], ld=0, rows_per_batch=0, row_off=0) -> RowM
 def gemm(a: Planes, w: Planes, n: int, *, a_batch: int, a_rows_per_batch: int, a_ld: int, m_per_batch: int,
          taps: int = 1, stride: int = 1, bias=None, gamma=None, residual: Optional[RowMap] = None, act=ACT_NONE,
          act2=ACT_NONE, out_f32: Optional[RowMap] = None, out_planes: Optional[Planes] = None,
-         out_planes_map=(0, 0, 0), simt: bool = False, dilation: int = 1):
+         out_planes_map=(0, 0, 0), simt: bool = False, dilation: int = 1, act_param=None, act2_param=None):
     """One dense contraction (see qb_gemm_desc).  Split mode iff both a.lo and w.lo are given."""
     split = a.lo is not None and w.lo is not None
     d = GemmDesc()
@@ -64,6 +64,7 @@ def gemm(a: Planes, w: Planes, n: int, *, a_batch: int, a_rows_per_batch: int, a
     d.bias, d.gamma = _p(bias), _p(gamma)
     d.residual = residual if residual is not None else RowMap(None, 0, 0, 0)
     d.act, d.act2 = act, act2
+    d.act_param, d.act2_param = _p(act_param), _p(act2_param)
     d.out_f32 = out_f32 if out_f32 is not None else RowMap(None, 0, 0, 0)
     if out_planes is not None:
         ld, rpb, off = out_planes_map
