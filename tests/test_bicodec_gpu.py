@@ -69,3 +69,31 @@ def test_bicodec_full_config_vs_oracle(lib):
         assert got.shape == (B, 1, T * 320) and e < TOL
     with pytest.raises(ValueError):
         m.detokenize(sem.cuda(), glob[:, :, :-1].cuda())
+
+
+def test_unise_sr_back_half_lm_to_waveform(lib):
+    """configs[2] back half (U/model/model.py:185-193): LLM_SFT.generate -> (global [B,32], semantic [B,T]) ->
+    BiCodec.detokenize(semantic, global[:, None]) -> wav; the LM's vocabularies are the codec's (4096 FSQ codes, 8192
+    semantic codes).  The waveform is checked against the oracle on the tokens the GPU LM produced."""
+    from oracle import bicodec as ob
+    from oracle import llama
+    from unified_audio_b200.llm import LLM_SFT
+    cfg_lm = llama.LM_FULL
+    lm = LLM_SFT(num_tasks=cfg_lm["num_tasks"], task_map=cfg_lm["task_map"], feats_dim=cfg_lm["feats_dim"],
+                 llm_base_config=cfg_lm["llm_base_config"])
+    lm.load_state_dict(llama.make_lm_state_dict(cfg_lm, 7, 2.0), strict=True)
+    lm = lm.cuda()
+    B, T = 2, 12
+    g = torch.Generator().manual_seed(5)
+    mix = torch.randn(B, T, 768, generator=g).cuda()
+    gids, sids = lm.generate("se", None, None, mix, mix, do_sample=False)
+    assert gids.shape == (B, 32) and sids.shape == (B, T)
+    assert int(gids.max()) < 4096 and int(sids.max()) < 8192 and int(gids.min()) >= 0 and int(sids.min()) >= 0
+    cfg = ob.BICODEC_FULL
+    codec, sd = build(cfg, 21)
+    wav = codec.detokenize(sids, gids[:, None, :])
+    torch.cuda.synchronize()
+    want = ob.detokenize(sd, cfg, sids.cpu(), gids[:, None, :].cpu())
+    e = rel(wav, want)
+    print(f"[UniSE SR back half] tokens -> wav rel {e:.2e}, {wav.shape[-1]} samples per clip")
+    assert wav.shape == (B, 1, T * 320) and e < TOL
