@@ -514,7 +514,13 @@ def main():
     wav_d, feat_d = wav_h.to(dev), feat_h.to(dev)
 
     # the public fixed-shape entry point: encode -> decode captured once in a CUDA graph (Codec.graphed), replayed per step
-    graphed = None if args.no_graph else model.graphed("roundtrip", wav_d, feat_d)
+    graphed = None
+    if not args.no_graph:
+        try:
+            graphed = model.graphed("roundtrip", wav_d, feat_d)
+        except Exception as e:      # same kernels either way: fall back to launching them one by one
+            print(f"[bench] CUDA-graph capture failed ({e!r}); launching kernel by kernel", file=sys.stderr)
+            torch.cuda.synchronize()
 
     def step_device():
         if graphed is not None:
