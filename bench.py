@@ -257,6 +257,7 @@ def run_lm(args):
             gather_tokens(torch.cat([gi, si], 1), world * B)
         return gi, si
 
+
     def timed(fn):
         if dist is not None:
             dist.barrier()
@@ -269,6 +270,45 @@ def run_lm(args):
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
+
+    if args.workload == "lm_forward":
+        # teacher-forced UniSE LM forward (llm_sft.py:37-89): prefix 252 + 284 code tokens per sequence, logits over the
+        # 12291-entry vocabulary, loss + accuracy - the "AR-LM forward" of north_star.  Tensor-bound; every GEMM is a 3-term split.
+        gt = torch.Generator().manual_seed(7 + rank)
+        gids_h = torch.randint(0, 4096, (B, 32), generator=gt).pin_memory()
+        sids_h = torch.randint(0, 8192, (B, T), generator=gt).pin_memory()
+        gids, sids = gids_h.to(dev), sids_h.to(dev)
+        L = 2 + T + 32 + 1 + T + 1            # task + mix_sos + feats, then sos/global/sos/semantic (+ eos target)
+        fwd = lambda a, b_, c_: m("se", None, None, a, a, b_, c_)
+        for _ in range(max(args.warmup, 3)):
+            fwd(mix, gids, sids)
+        ops.launch_count_reset()
+        ms = timed(lambda: fwd(mix, gids, sids))
+        launches = ops.launch_count()
+
+        def e2e_fwd():
+            loss, acc = fwd(mix_h.to(dev, non_blocking=True), gids_h.to(dev, non_blocking=True), sids_h.to(dev, non_blocking=True))
+            loss.cpu(); acc.cpu()
+        ms_e2e = timed(e2e_fwd)
+        if rank == 0:
+            peaks = load_peaks()
+            per_tok = 12 * 2 * (4 * 512 * 512 + 3 * 512 * 2048)
+            flops = world * B * (L * per_tok + 12 * 4 * 512 * L * L / 2 + 2 * 768 * 512 * T + (T + 34) * 2 * 512 * 12291)
+            tf = flops / (ms * 1e-3) / 1e12
+            print(json.dumps(dict(
+                metric="unise_lm_forward_tokens_per_s", value=world * B * L / (ms * 1e-3), unit="tokens/s", n_gpus=world,
+                steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f16x3 split tensor-core (fp32-grade), f32 accumulate", data="synthetic",
+                config=dict(workload=f"UniSE LM teacher-forced forward, {B} sequences x {L} positions per GPU, logits + loss", batch=B * world,
+                            positions=L, parallelism=f"dp{world}"),
+                e2e=dict(value=world * B * L / (ms_e2e * 1e-3), unit="tokens/s", ms_per_step=ms_e2e,
+                         h2d_bytes_per_step=int(mix_h.numel() * 4 + gids_h.numel() * 8 + sids_h.numel() * 8) * world, d2h_bytes_per_step=8 * world),
+                gpu_launches=int(launches),
+                roofline=dict(bound="tensor", achieved=tf, peak=peaks["tf_sus"] * world, unit="TFLOP/s", frac=tf / (peaks["tf_sus"] * world),
+                              traffic=None, kernel="whole forward, algorithmic FLOPs (every GEMM and the attention issued 3x: ceiling 1/3)"))))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     for _ in range(max(args.warmup, 1)):
         step(mix)
@@ -469,14 +509,14 @@ def main():
     ap.add_argument("--precision", default="mixed")
     ap.add_argument("--ref-clips", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="codec", choices=["codec", "lm", "bicodec"],
+    ap.add_argument("--workload", default="codec", choices=["codec", "lm", "lm_forward", "bicodec"],
                     help="codec = BASELINE configs[1] (default, the driver's line); lm = UniSE SR AR-LM generate (configs[2]); "
                          "bicodec = BiCodec detokenize, the decoder UniSE feeds the LM tokens to")
     ap.add_argument("--quick", action="store_true", help="profiling aid: W warm-up + K steps only, no e2e/roofline/cpu legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     cfg = H2_FULL
-    if args.workload == "lm":
+    if args.workload in ("lm", "lm_forward"):
         return run_lm(args)
     if args.workload == "bicodec":
         return run_bicodec(args)

@@ -53,9 +53,22 @@ struct GemmParams {
 };
 
 // Snake (bicodec/modules/blocks/layers.py:33-38): x + (alpha + 1e-9)^-1 * sin(alpha x)^2
+// Epilogue form: sin.approx after an explicit 2*pi range reduction (|error| < 3e-7 for |alpha x| < 64, exact sinf beyond) and
+// rcp.approx (1 ulp) - the accurate sinf + IEEE division cost 35 instructions per element and made the N < 256 conv GEMMs
+// epilogue-bound.
 __device__ __forceinline__ float snake_f(float v, float a) {
-  const float sn = sinf(a * v);
-  return fmaf(1.0f / (a + 1e-9f), sn * sn, v);
+  const float t = a * v;
+  float sn;
+  if (fabsf(t) < 64.f) {
+    const float k = rintf(t * 0.15915494309189535f);
+    const float r = fmaf(k, -6.2831854820251465f, t);            // t - k * fl(2 pi)
+    sn = __sinf(fmaf(k, 1.7484555e-7f, r));                      // + k * (fl(2 pi) - 2 pi)
+  } else {
+    sn = sinf(t);
+  }
+  float rc;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(a + 1e-9f));
+  return fmaf(rc, sn * sn, v);
 }
 __device__ __forceinline__ float apply_act(int act, float v) {
   if (act == QB_ACT_GELU) return gelu_fast(v);
