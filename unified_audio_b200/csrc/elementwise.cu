@@ -267,6 +267,67 @@ __global__ void groupnorm_stats_kernel(const float* __restrict__ x, int T, int C
   }
 }
 
+// float4 variants (C and C/G multiples of 4): 16-byte loads, fp64 accumulation kept (the variance is E[x^2] - mean^2)
+__global__ void groupnorm_stats_v4_kernel(const float4* __restrict__ x, int T, int C4, int G, float eps,
+                                          float* __restrict__ stats) {
+  const int g = blockIdx.x, b = blockIdx.y, cpg4 = C4 / G;
+  const float4* xb = x + (long long)b * T * C4 + g * cpg4;
+  const int n4 = T * cpg4;
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const int r = i / cpg4, c = i - r * cpg4;
+    const float4 v = xb[(long long)r * C4 + c];
+    s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+    q += ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w);
+  }
+  __shared__ double ss[32], sq[32];
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sq[threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S = 0, Q = 0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) { S += ss[i]; Q += sq[i]; }
+    const double n = 4.0 * n4, mean = S / n;
+    double var = Q / n - mean * mean;
+    if (var < 0) var = 0;
+    stats[((long long)b * G + g) * 2] = (float)mean;
+    stats[((long long)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+__global__ void groupnorm_apply_v4_kernel(const float4* __restrict__ x, const float* __restrict__ stats,
+                                          const float4* __restrict__ w, const float4* __restrict__ bz, int T, int C4, int cpg4,
+                                          int G, int swish, float4* __restrict__ out, __half* __restrict__ hi,
+                                          __half* __restrict__ lo, long long ld, long long rpb, long long off, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = (int)(i % C4);
+  const long long r = i / C4;
+  const int t = (int)(r % T);
+  const long long b = r / T;
+  const float2 st = *reinterpret_cast<const float2*>(stats + (b * G + c4 / cpg4) * 2);
+  const float4 xv = x[i], wv = __ldg(w + c4), bv = __ldg(bz + c4);
+  float v[4] = {(xv.x - st.x) * st.y * wv.x + bv.x, (xv.y - st.x) * st.y * wv.y + bv.y,
+                (xv.z - st.x) * st.y * wv.z + bv.z, (xv.w - st.x) * st.y * wv.w + bv.w};
+  if (swish) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = v[e] * sigmoid_acc(v[e]);
+  }
+  if (out) out[i] = make_float4(v[0], v[1], v[2], v[3]);
+  if (hi) {
+    __half h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_f16(v[e], h[e], l[e]);
+    const long long o = ((b * rpb + off + t) * ld) / 4 + c4;          // ld is a multiple of 4 on this path
+    __half2 hh[2] = {__halves2half2(h[0], h[1]), __halves2half2(h[2], h[3])};
+    reinterpret_cast<uint2*>(hi)[o] = *reinterpret_cast<uint2*>(hh);
+    if (lo) {
+      __half2 ll[2] = {__halves2half2(l[0], l[1]), __halves2half2(l[2], l[3])};
+      reinterpret_cast<uint2*>(lo)[o] = *reinterpret_cast<uint2*>(ll);
+    }
+  }
+}
+
 __global__ void groupnorm_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats,
                                        const float* __restrict__ w, const float* __restrict__ bz, int T, int C, int G,
                                        int swish, float* __restrict__ out, __half* __restrict__ hi,
@@ -590,6 +651,10 @@ extern "C" int qb_groupnorm_stats(const float* x, int64_t B, int64_t T, int64_t 
                                   float* stats, void* stream) {
   QB_REQUIRE(x && stats && C % groups == 0, "groupnorm_stats: bad args");
   dim3 grid((unsigned)groups, (unsigned)B);
+  if (C % 4 == 0 && (C / groups) % 4 == 0) {
+    groupnorm_stats_v4_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>((const float4*)x, (int)T, (int)(C / 4), groups, eps, stats);
+    QB_LAUNCH_END();
+  }
   groupnorm_stats_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(x, (int)T, (int)C, groups, eps, stats);
   QB_LAUNCH_END();
 }
@@ -599,6 +664,13 @@ extern "C" int qb_groupnorm_apply(const float* x, const float* stats, const floa
                                   qb_half* lo, int64_t ld, int64_t rows_per_batch, int64_t row_off, void* stream) {
   QB_REQUIRE(x && stats && w && b && (out_f32 || hi), "groupnorm_apply: bad args");
   QB_REQUIRE(!hi || (C <= ld && row_off + T <= rows_per_batch), "groupnorm_apply: plane buffer too small");
+  if (C % 4 == 0 && (C / groups) % 4 == 0 && (!hi || ld % 4 == 0)) {
+    const long long total = B * T * (C / 4);
+    groupnorm_apply_v4_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)x, stats, (const float4*)w, (const float4*)b, (int)T, (int)(C / 4), (int)(C / groups / 4), groups, swish,
+        (float4*)out_f32, (__half*)hi, (__half*)lo, ld, rows_per_batch, row_off, total);
+    QB_LAUNCH_END();
+  }
   dim3 grid((unsigned)T, (unsigned)B);
   groupnorm_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, stats, w, b, (int)T, (int)C, groups, swish, out_f32,
                                                                 (__half*)hi, (__half*)lo, ld, rows_per_batch, row_off);

@@ -707,7 +707,11 @@ extern "C" int qb_gemm(const qb_gemm_desc* d, void* stream) {
   const int sms = num_sms_cached();
   // CTA pairs (256-row tiles) when they do not add row padding and the N extent fills a 256-wide tile
   static const int pair_mode = getenv("QB_GEMM_PAIR") ? atoi(getenv("QB_GEMM_PAIR")) : 1;
-  const bool pair_ok = pair_mode && d->n >= 256 && (ceil_div(d->m_per_batch, 256) * 2 == ceil_div(d->m_per_batch, 128));
+  // (a pair tile that is 3/4 full in N still halves the operand bytes each SM ingests per MMA; up to 3 % of padded rows
+  //  per batch are accepted - the 1-CTA kernel is ingest-bound on every conv shape of the BiCodec generator)
+  const long long m256 = ceil_div(d->m_per_batch, 256) * 256;
+  const bool pair_ok = pair_mode && d->n >= 192 &&
+                       (ceil_div(d->m_per_batch, 256) * 2 == ceil_div(d->m_per_batch, 128) || m256 * 100 <= d->m_per_batch * 103);
   if (pair_ok) return split ? launch_tc2<256, 3, 3>(d, st, sms) : launch_tc2<256, 1, 6>(d, st, sms);
   if (!split) return bn == 256 ? launch_tc<256, 1, 4>(d, st, sms) : launch_tc<128, 1, 6>(d, st, sms);
   return bn == 256 ? launch_tc<256, 3, 2>(d, st, sms) : launch_tc<128, 3, 3>(d, st, sms);

@@ -37,13 +37,6 @@ __device__ __forceinline__ unsigned lt_ld_acquire(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3,
-                                            int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
 // linear bulk copy global -> shared (no tensor map): the published h is stored tile-native (pre-swizzled)
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -57,7 +50,7 @@ __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[
 
 template <int U>
 __global__ void __launch_bounds__(LT_THREADS, 1)
-lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
+lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW,
                const float* __restrict__ xp, int B, int T, int H, __half* __restrict__ out_hi,
                __half* __restrict__ out_lo, __half* hbuf, unsigned* flags, int Bp, int n_groups, long long* prof) {
   constexpr int N = 4 * U;                      // gate rows of this CTA = UMMA N
@@ -100,7 +93,6 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     // ===================== TMA producer =====================
     if (lane == 0) {
       prefetch_tmap(&tmW);
-      prefetch_tmap(&tmH);
       mbar_arrive_expect_tx(wbar, (uint32_t)KB * WBLK);
       for (int kb = 0; kb < KB; ++kb) tma_load_2d(Wsm + (size_t)kb * WBLK, &tmW, wbar, kb * 64, blockIdx.x * N);
     }
@@ -281,7 +273,7 @@ static int lstm_tc_chunk(const float* xp, const qb_half* whh_perm, int U, int B,
   const int n_groups = (B + 31) / 32, Bp = n_groups * 32;
   EncodeTiledFn enc = lt_encode();
   QB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available");
-  CUtensorMap tmW, tmH;
+  CUtensorMap tmW;
   {
     cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)(4 * H)};
     cuuint64_t str[1] = {(cuuint64_t)H * 2};
@@ -291,17 +283,8 @@ static int lstm_tc_chunk(const float* xp, const qb_half* whh_perm, int U, int B,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     QB_REQUIRE(r == CUDA_SUCCESS, "lstm_tc: W tensor map failed (%d)", (int)r);
   }
+  // published h: tile-native [buffer][group][K-block][32 rows][128 B] (pre-swizzled), read with linear bulk copies
   __half* hbuf = (__half*)workspace;
-  {
-    // 5-D view (k within block, row within group, K-block, buffer, group): one box = LT_KG K-block tiles of a group
-    cuuint64_t dims[5] = {64, 32, (cuuint64_t)(H / 64), 2, (cuuint64_t)n_groups};
-    cuuint64_t str[4] = {(cuuint64_t)H * 2, 128, (cuuint64_t)Bp * H * 2, (cuuint64_t)32 * H * 2};
-    cuuint32_t box[5] = {64, 32, LT_KG, 1, 1};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(&tmH, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)hbuf, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    QB_REQUIRE(r == CUDA_SUCCESS, "lstm_tc: h tensor map failed (%d)", (int)r);
-  }
   const size_t smem = (size_t)KB * N * 128 + (size_t)LT_STAGES * LT_SLOT + LT_PAD + 1024 + 256;
   QB_REQUIRE(smem <= 227 * 1024, "lstm_tc: shared memory budget exceeded (%zu)", smem);
   const size_t hbytes = (size_t)2 * Bp * H * 2;
@@ -310,7 +293,7 @@ static int lstm_tc_chunk(const float* xp, const qb_half* whh_perm, int U, int B,
   static long long* prof = nullptr;
   if (!prof && getenv("QB_LSTM_PROF")) { cudaMalloc(&prof, 64); cudaMemset(prof, 0, 64); }
   int Bi = B, Ti = (int)T, Hi = (int)H, Bpi = Bp, ng = n_groups;
-  void* args[] = {&tmW, &tmH, &xp, &Bi, &Ti, &Hi, &oh, &ol, &hbuf, &flags, &Bpi, &ng, &prof};
+  void* args[] = {&tmW, &xp, &Bi, &Ti, &Hi, &oh, &ol, &hbuf, &flags, &Bpi, &ng, &prof};
   const void* fn = U == 4 ? (const void*)lstm_tc_kernel<4> : U == 8 ? (const void*)lstm_tc_kernel<8> : (const void*)lstm_tc_kernel<12>;
   QB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   QB_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LT_THREADS), args, smem, st));
