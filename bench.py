@@ -204,6 +204,8 @@ def run_lm(args):
               llm_base_config=dict(cond_dim=80, global_size=4096, semantic_size=8192, hidden_size=512, num_layers=12,
                                    num_attention_heads=8, dropout_p=0.1, max_position_embeddings=4096, label_smoothing=0.1))
     B, T = 32, 250
+    if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
+        return
     if args.impl == "reference":
         from oracle import llama
         sd = llama.make_lm_state_dict(LM, 7, 2.0)
@@ -371,6 +373,8 @@ def run_bicodec(args):
     """Secondary line: BiCodec.detokenize, the decoder UniSE feeds its AR-LM tokens to (configs[2] back half):
     B=32 clips x 250 semantic tokens + 32 global tokens -> 5 s @ 16 kHz each."""
     B, T = 32, 250
+    if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
+        return
     if args.impl == "reference":
         from oracle import bicodec as ob
         cfg = ob.BICODEC_FULL
