@@ -32,9 +32,11 @@ constexpr uint32_t LT_KBLK = 32 * 128;            // one K-block of one group: 3
 constexpr uint32_t LT_SLOT = LT_KBLK * LT_KG;
 constexpr uint32_t LT_PAD = 12 * 1024;            // A tiles read up to 12 KB past a group-0 K-block
 
-__device__ __forceinline__ unsigned lt_ld_acquire(const unsigned* p) {
+// flag polling: relaxed loads (the four of a lane are independent and in flight together - acquire loads would serialise
+// into four L2 round trips per poll), one acquire fence once every flag has been seen
+__device__ __forceinline__ unsigned lt_ld_relaxed(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 // linear bulk copy global -> shared (no tensor map): the published h is stored tile-native (pre-swizzled)
@@ -116,11 +118,13 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW,
         unsigned spins = 0;
         for (;;) {
           bool ok = true;
-          for (int c = lane; c < G; c += 32) ok = ok && (lt_ld_acquire(fl + c) >= (unsigned)t);
+          for (int c = lane; c < G; c += 32) ok = ok && (lt_ld_relaxed(fl + c) >= (unsigned)t);
           if (__all_sync(0xffffffffu, ok)) break;
           __nanosleep(64);                                      // back off: 128 CTAs polling the same 4 lines
           if (++spins > (1u << 24)) asm volatile("trap;");
         }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");        // acquire side of the flags every lane has just observed
+        __syncwarp();
         pw += clock64() - c0;
         if (lane == 0) {
           ts_flag[g] = clock64();
@@ -241,8 +245,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW,
         tc_fence_before();
         asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory");
         const long long e2 = clock64();
-        if (half == 0 && lane == 0) {
-          __threadfence();
+        if (half == 0 && lane == 0) {   // release is cumulative over the group's h stores ordered before it by the bar.sync
           asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + (size_t)g * G + blockIdx.x), "r"((unsigned)(t + 1))
                        : "memory");
         }
