@@ -145,7 +145,7 @@ def test_product_does_not_import_oracle():
 
 def test_precision_policies_cover_every_gemm_group():
     from unified_audio_b200.codec import PRECISION_POLICIES
-    groups = {"convnext", "lstm_attn", "mlp", "conv", "head", "dft"}
+    groups = {"convnext", "lstm_attn", "mlp", "mlp_dec", "conv", "head", "dft"}
     for name, pol in PRECISION_POLICIES.items():
         assert set(pol) == groups, name
     assert all(PRECISION_POLICIES["accurate"].values())
