@@ -23,6 +23,11 @@ real package exists to check against.  What this file follows:
 
 State-dict layout mirrors upstream: `layers.{i}._codebook.{initted, cluster_size,
 embed_avg, embed}`.
+
+Partial pin (oracle/make_golden_rvq.py): the reference's IN-TREE residual VQ of the same family,
+`HCodec-2.0/vq/core_vq.py` `ResidualVectorQuantization` (lines 223-238, 394-412), loaded with the same seeded
+codebooks, returns exactly the indices and de-quantised vectors of `rvq_encode` / `rvq_decode` (150 rows x 4 layers and
+80 rows x 16 layers x 4096 codes: 100 % identical); its outputs are committed as tests/golden/rvq_intree.npz.
 """
 from __future__ import annotations
 

@@ -205,3 +205,14 @@ def test_bicodec_oracle_matches_reference_fixture_and_spec_keys():
     spec = {k: list(v) for k, v in bicodec_spec(BICODEC_CONFIG).items()}
     assert spec == keys
     assert {k: list(v[0]) for k, v in ob.param_specs(ob.BICODEC_FULL).items()} == keys
+
+
+def test_oracle_rvq_matches_reference_in_tree_residual_vq():
+    """tests/golden/rvq_intree.npz holds indices / reconstructions of the reference's IN-TREE residual VQ
+    (HCodec-2.0/vq/core_vq.py ResidualVectorQuantization, oracle/make_golden_rvq.py); the oracle reproduces them exactly."""
+    from oracle import rvq
+    z = np.load(os.path.join(GOLD, "rvq_intree.npz"))
+    x, cb = torch.from_numpy(z["x"]), torch.from_numpy(z["codebooks"])
+    idx, quant = rvq.rvq_encode(x, cb)
+    assert torch.equal(idx, torch.from_numpy(z["ref_indices"]))
+    assert float((rvq.rvq_decode(idx, cb) - torch.from_numpy(z["ref_dequant"])).abs().max()) < 1e-6
