@@ -216,3 +216,20 @@ def test_oracle_rvq_matches_reference_in_tree_residual_vq():
     idx, quant = rvq.rvq_encode(x, cb)
     assert torch.equal(idx, torch.from_numpy(z["ref_indices"]))
     assert float((rvq.rvq_decode(idx, cb) - torch.from_numpy(z["ref_dequant"])).abs().max()) < 1e-6
+
+
+def test_oracle_hubert_front_end_matches_fixture():
+    """SSL front end (groundwork): oracle/hubert.py reproduces transformers.HubertModel's mean hidden state and
+    torchaudio's 48k -> 16k resampler on the committed fixture (oracle/make_golden_hubert.py)."""
+    from oracle import hubert as oh
+    z = np.load(os.path.join(GOLD, "hubert_small.npz"))
+    meta = json.loads(str(z["meta"]))
+    c = oh.hubert_small()
+    sd = oh.make_state_dict(c, meta["seed"])
+    hs = oh.hubert_hidden_states(sd, c, torch.from_numpy(z["wav"]))
+    mix = torch.stack(hs, 1).mean(1)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    assert rel(mix, torch.from_numpy(z["mix"])) < 1e-5 and rel(hs[-1], torch.from_numpy(z["last"])) < 1e-5
+    w48 = torch.from_numpy(z["wav48"])
+    assert rel(oh.resample(w48), torch.from_numpy(z["resampled"])) < 1e-6
+    assert rel(oh.extract_ssl_features(sd, c, w48), torch.from_numpy(z["feats"])) < 1e-5
