@@ -180,3 +180,103 @@ def extract_ssl_features(sd, c, wav48k, compress=True):
     if compress:
         mix = ((mix > 0).float() * 2 - 1) * mix.abs() ** 0.3
     return mix
+
+
+# --------------------------------------------------------------------------- WavLM-base-plus (UniSE, U/model/model.py:30,38-51)
+# Same feature encoder / projection / positional conv / post-LN layers as HuBERT-base; the attention adds a gated relative
+# position bias (transformers.models.wavlm.modeling_wavlm.WavLMAttention): a bucketed embedding [320, heads] owned by layer 0
+# and shared by all layers, scaled per query by a gate computed from the layer input.
+WAVLM_BASE_PLUS = dict(HUBERT_BASE, num_buckets=320, max_distance=800)
+
+
+def wavlm_small():
+    return dict(hubert_small(), num_buckets=32, max_distance=80)
+
+
+def wavlm_param_specs(c):
+    out = OrderedDict()
+    for k, v in param_specs(c).items():
+        out[k] = v
+    h, d = c["heads"], c["hidden"] // c["heads"]
+    for i in range(c["layers"]):
+        p = f"encoder.layers.{i}.attention."
+        out[p + "gru_rel_pos_const"] = ((1, h, 1, 1), "nw")
+        out[p + "gru_rel_pos_linear.weight"] = ((8, d), "w"); out[p + "gru_rel_pos_linear.bias"] = ((8,), "b")
+    out["encoder.layers.0.attention.rel_attn_embed.weight"] = ((c["num_buckets"], h), "emb")
+    return out
+
+
+def wavlm_make_state_dict(c, seed=0):
+    sd = make_state_dict(c, seed)
+    for name, (shape, kind) in wavlm_param_specs(c).items():
+        if name in sd:
+            continue
+        g = _gen(seed, name)
+        if kind == "w":
+            sd[name] = torch.randn(shape, generator=g) * (1.5 / shape[-1]) ** 0.5
+        elif kind == "b":
+            sd[name] = 0.05 * torch.randn(shape, generator=g)
+        elif kind == "nw":
+            sd[name] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif kind == "emb":
+            sd[name] = 0.5 * torch.randn(shape, generator=g)
+    return sd
+
+
+def wavlm_position_bias(sd, c, T):
+    """WavLMAttention.compute_bias / _relative_positions_bucket -> [heads, T, T]"""
+    rel = torch.arange(T)[None, :] - torch.arange(T)[:, None]
+    nb = c["num_buckets"] // 2
+    bucket = (rel > 0).long() * nb
+    a = rel.abs()
+    max_exact = nb // 2
+    large = torch.log(a.float() / max_exact) / math.log(c["max_distance"] / max_exact) * (nb - max_exact)
+    large = torch.min((max_exact + large).long(), torch.full_like(a, nb - 1))
+    bucket = bucket + torch.where(a < max_exact, a, large)
+    return F.embedding(bucket, sd["encoder.layers.0.attention.rel_attn_embed.weight"]).permute(2, 0, 1)
+
+
+def wavlm_encoder_layer(sd, p, c, x, pos_bias):
+    B, T, H = x.shape
+    h, d = c["heads"], H // c["heads"]
+    lin = lambda n, t: F.linear(t, sd[p + f"{n}.weight"], sd[p + f"{n}.bias"])
+    xh = x.view(B, T, h, d).permute(0, 2, 1, 3)                                        # gate from the layer INPUT, per head
+    proj = lin("attention.gru_rel_pos_linear", xh).view(B, h, T, 2, 4).sum(-1)
+    ga, gb = torch.sigmoid(proj).chunk(2, dim=-1)
+    gate = ga * (gb * sd[p + "attention.gru_rel_pos_const"] - 1.0) + 2.0                # [B,h,T,1]
+    bias = gate * pos_bias[None]                                                       # [B,h,T,T]
+    q = lin("attention.q_proj", x).view(B, T, h, d).transpose(1, 2)
+    k = lin("attention.k_proj", x).view(B, T, h, d).transpose(1, 2)
+    v = lin("attention.v_proj", x).view(B, T, h, d).transpose(1, 2)
+    a = torch.softmax((q * d ** -0.5) @ k.transpose(-1, -2) + bias, -1) @ v            # F.multi_head_attention_forward
+    x = x + lin("attention.out_proj", a.transpose(1, 2).reshape(B, T, H))
+    x = F.layer_norm(x, (H,), sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"], c["eps"])
+    f = lin("feed_forward.output_dense", F.gelu(lin("feed_forward.intermediate_dense", x)))
+    return F.layer_norm(x + f, (H,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], c["eps"])
+
+
+@torch.no_grad()
+def wavlm_hidden_states(sd, c, wav):
+    feats = feature_encoder(sd, c, wav).transpose(1, 2)
+    Cc = feats.shape[-1]
+    x = F.layer_norm(feats, (Cc,), sd["feature_projection.layer_norm.weight"], sd["feature_projection.layer_norm.bias"], c["eps"])
+    x = F.linear(x, sd["feature_projection.projection.weight"], sd["feature_projection.projection.bias"])
+    pos = F.conv1d(x.transpose(1, 2), pos_conv_weight(sd), sd["encoder.pos_conv_embed.conv.bias"], padding=c["pos_k"] // 2,
+                   groups=c["pos_groups"])
+    if c["pos_k"] % 2 == 0:
+        pos = pos[:, :, :-1]
+    x = x + F.gelu(pos).transpose(1, 2)
+    H = x.shape[-1]
+    x = F.layer_norm(x, (H,), sd["encoder.layer_norm.weight"], sd["encoder.layer_norm.bias"], c["eps"])
+    pb = wavlm_position_bias(sd, c, x.shape[1])
+    hs = [x]
+    for i in range(c["layers"]):
+        x = wavlm_encoder_layer(sd, f"encoder.layers.{i}.", c, x, pb)
+        hs.append(x)
+    return hs
+
+
+@torch.no_grad()
+def extract_semantic_features(sd, c, wav16k):
+    """U/model/model.py:38-51: pad 160 each side, mean of the 13 WavLM hidden states (no compression)"""
+    return torch.stack(wavlm_hidden_states(sd, c, F.pad(wav16k, (160, 160))), 1).mean(1)

@@ -233,3 +233,29 @@ def test_oracle_hubert_front_end_matches_fixture():
     w48 = torch.from_numpy(z["wav48"])
     assert rel(oh.resample(w48), torch.from_numpy(z["resampled"])) < 1e-6
     assert rel(oh.extract_ssl_features(sd, c, w48), torch.from_numpy(z["feats"])) < 1e-5
+
+
+def test_oracle_wavlm_and_unise_sr_chain():
+    """WavLM-base-plus restatement against the transformers fixture, then the whole UniSE SR chain on the oracles:
+    wav -> WavLM mean hidden state -> LLM_SFT.generate -> BiCodec.detokenize -> wav (U/model/model.py:175-193)."""
+    from oracle import bicodec as ob
+    from oracle import hubert as oh
+    from oracle import llama
+    z = np.load(os.path.join(GOLD, "wavlm_small.npz"))
+    meta = json.loads(str(z["meta"]))
+    c = oh.wavlm_small()
+    sd = oh.wavlm_make_state_dict(c, meta["seed"])
+    mix = torch.stack(oh.wavlm_hidden_states(sd, c, torch.from_numpy(z["wav"])), 1).mean(1)
+    assert float((mix - torch.from_numpy(z["mix"])).abs().max() / torch.from_numpy(z["mix"]).abs().max()) < 1e-5
+    # chain at reduced widths: 0.32 s of 16 kHz audio -> 16 frames -> 32 global + 16 semantic tokens -> 16 * 320 samples
+    wav = 0.1 * torch.randn(2, 16 * 320, generator=torch.Generator().manual_seed(1))
+    feats = oh.extract_semantic_features(sd, c, wav)
+    assert feats.shape == (2, 16, c["hidden"])
+    bc = ob.bicodec_small()
+    lm_cfg = llama.lm_small(hidden=128, layers=2, heads=2, gsize=4096, ssize=bc["quantizer"]["codebook_size"], feats=c["hidden"])
+    lm_sd = llama.make_lm_state_dict(lm_cfg, 3, 1.0)
+    gids, sids = llama.sft_generate(lm_sd, lm_cfg, "se", None, feats, feats.shape[1])
+    assert gids.shape == (2, 32) and sids.shape == (2, 16)
+    # the small BiCodec has 8 global tokens: take the first 8 of the 32 generated (shipped: 32 of 32)
+    out = ob.detokenize(ob.make_state_dict(bc, 4), bc, sids, gids[:, None, :bc["speaker"]["token_num"]])
+    assert out.shape == (2, 1, 16 * 320) and bool(torch.isfinite(out).all())
