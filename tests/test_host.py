@@ -259,3 +259,23 @@ def test_oracle_wavlm_and_unise_sr_chain():
     # the small BiCodec has 8 global tokens: take the first 8 of the 32 generated (shipped: 32 of 32)
     out = ob.detokenize(ob.make_state_dict(bc, 4), bc, sids, gids[:, None, :bc["speaker"]["token_num"]])
     assert out.shape == (2, 1, 16 * 320) and bool(torch.isfinite(out).all())
+
+
+def test_c_abi_reports_errors_without_exceptions(lib):
+    """Error behaviour of the boundary: bad arguments return a negative code and leave a message in qb_last_error();
+    nothing is launched and no C++ exception crosses the ABI (checked here without a GPU: validation precedes every CUDA call)."""
+    import ctypes as C
+    from unified_audio_b200._lib import GemmDesc
+    assert lib.qb_gemm(None, None) < 0 and b"null desc" in lib.qb_last_error()
+    d = GemmDesc()                                     # all-zero descriptor: null operands
+    assert lib.qb_gemm(C.byref(d), None) < 0 and b"null operand" in lib.qb_last_error()
+    one = C.c_void_p(16)                               # non-null dummy pointers: rejected by shape checks before any use
+    d.a_hi, d.w_hi, d.a_ld, d.taps, d.stride = one, one, 48, 1, 1
+    assert lib.qb_gemm(C.byref(d), None) < 0 and b"multiple of 64" in lib.qb_last_error()
+    rc = lib.qb_lm_decode_layer_tc(one, 33, 512, 8, 2048, one, one, one, one, one, one, one, 64, one, one, one, one, one, one, None)
+    assert rc < 0 and b"batch must be 1..32" in lib.qb_last_error()
+    rc = lib.qb_lm_head_argmax_tc(one, 4, 512, one, one, 100, one, one, one, 8, one, one, one, one, None)
+    assert rc < 0 and b"multiple of 16" in lib.qb_last_error()
+    rc = lib.qb_snake_planes(one, 0, one, 1, 8, 96, one, None, 64, 8, 0, None)          # C > ld
+    assert rc < 0 and b"snake_planes" in lib.qb_last_error()
+    assert lib.qb_version() > 0
