@@ -679,7 +679,8 @@ def main():
                       peak_source=f"{peaks['src']} dense bf16 burst (fp16 shares the pipe)",
                       path_algorithmic_tflops=path_tf, path_frac_of_sustained=path_tf / peaks["tf_sus"]),
     )
-    if not args.no_cpu_baseline:
+    line["cpu_baseline"] = None                  # timed on rank 0 at N = 1 only (the N > 1 lines carry the key, empty)
+    if not args.no_cpu_baseline and world == 1:
         sd_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()}
         v, dt = cpu_baseline(sd_cpu, cfg, args.seconds, 1)
         line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=_BEST_THREADS, kind="port",
