@@ -207,6 +207,8 @@ class LLM_SFT(nn.Module):
             cache = StaticKVCache(self.n_layers, B, self.heads, max(64, -(-L // 64) * 64 + (1024 if use_cache else 0)), self._dev())
         x = inputs_embeds.float().reshape(B * L, H).contiguous().clone()
         if L == 1 and B <= 32 and cache.length > 0:
+            if cache.length + 1 > cache.Lmax:
+                raise ValueError("KV cache too small")
             self._decode_layers(x, B, cache)
             cache.length += 1
             cache.pos.fill_(cache.length)
