@@ -279,3 +279,21 @@ def test_c_abi_reports_errors_without_exceptions(lib):
     rc = lib.qb_snake_planes(one, 0, one, 1, 8, 96, one, None, 64, 8, 0, None)          # C > ld
     assert rc < 0 and b"snake_planes" in lib.qb_last_error()
     assert lib.qb_version() > 0
+
+
+def test_oracle_adaptive_alignment_matches_reference_fixture():
+    """H-Codec-1.5 groundwork: similarity alignment / length packing / de-aggregation restatements against
+    alignment matrices produced by the reference's own FlexiCodec static methods (oracle/make_golden_adaptive.py)."""
+    from oracle import adaptive as oa
+    z = np.load(os.path.join(GOLD, "adaptive_alignment.npz"))
+    h = torch.from_numpy(z["h"])
+    for thr in (0.6, 0.85):
+        a, sim, n = oa.similarity_alignment(h, thr, 8)
+        assert torch.equal(a, torch.from_numpy(z[f"align_{thr}"]))
+        lens = oa.token_lengths(a)
+        assert int(lens.max()) <= 8 and bool((lens.sum(1) == h.shape[1]).all())
+        codes = torch.randint(0, 1024, (h.shape[0], 4, a.shape[1]))
+        plain, l2 = oa.extract_lengths(oa.inject_lengths(codes, lens.clamp(min=1), 1024), 1024)
+        assert torch.equal(plain, codes) and torch.equal(l2, lens.clamp(min=1))
+        grouped = torch.randn(h.shape[0], 5, a.shape[1]) * (lens > 0)[:, None]
+        assert torch.equal(oa.deaggregate(grouped, a)[:, :, : int(lens[0].sum())][0], oa.deaggregate_by_lengths(grouped, lens)[0])
