@@ -122,126 +122,145 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
-_BEST_THREADS = None
+LM_CFG = dict(num_tasks=3, task_map=dict(se=0, tse=1, rtse=2), feats_dim=768,
+              llm_base_config=dict(cond_dim=80, global_size=4096, semantic_size=8192, hidden_size=512, num_layers=12,
+                                   num_attention_heads=8, dropout_p=0.1, max_position_embeddings=4096, label_smoothing=0.1))
+REF_THREADS = 32        # pinned host thread count of every CPU leg (no per-run calibration)
 
 
-def _best_threads(sd, cfg):
-    """Pick the host thread count that makes the reference's CPU path fastest (short calibration on a
-    0.8 s clip): on a many-core shared host `all cores` is often far slower than a moderate count."""
-    global _BEST_THREADS
-    if _BEST_THREADS is None:
-        from oracle import hcodec2
-        try:
-            avail = len(os.sched_getaffinity(0))
-        except Exception:
-            avail = os.cpu_count() or 1
-        g = torch.Generator().manual_seed(3)
-        wav = 0.1 * torch.randn(1, 38400, generator=g)
-        feat = torch.randn(1, 768, 40, generator=g)
-        best = (1e30, 1)
-        for n in sorted({min(avail, c) for c in (8, 16, 32, 64, avail)}):
-            torch.set_num_threads(n)
-            hcodec2.codec_encode(sd, cfg, wav, feat)   # warm
-            t0 = time.perf_counter()
-            hcodec2.codec_encode(sd, cfg, wav, feat)
-            dt = time.perf_counter() - t0
-            if dt < best[0]:
-                best = (dt, n)
-        _BEST_THREADS = best[1]
-    return _BEST_THREADS
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
-def cpu_baseline(model_sd_cpu, cfg, seconds, clips):
-    """The reference's own PyTorch CPU path (oracle port, pinned bit-exact against the reference
-    modules) on this box's host cores, on a bounded sample of the same workload."""
+def cpu_threads():
+    n = min(REF_THREADS, host_cores())
+    torch.set_num_threads(n)
+    return n
+
+
+class Ctx:
+    """One process per GPU (torchrun env); NCCL only for the barrier, the max-over-ranks timing and the token gather."""
+
+    def __init__(self):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist_
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+                os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
+            dist_.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist_
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """K steps bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks -> ms / step"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.dist is not None:
+            t = torch.tensor([ms], device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms / steps
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs (oracle port)
+def cpu_codec(sd_cpu, cfg, wav, feat, want_codes=False):
+    """The reference's own PyTorch CPU path (oracle port, pinned bit-exact against the reference modules) on this box's
+    host cores: encode + RVQ + decode of the given clips.  -> (samples/s, seconds, taps, codes)"""
     from oracle import hcodec2
-    torch.set_num_threads(_best_threads(model_sd_cpu, cfg))
-    T = int(seconds * cfg["sampling_rate"])
+    cpu_threads()
+    taps = {} if want_codes else None
+    t0 = time.perf_counter()
+    ac, sc = hcodec2.codec_encode(sd_cpu, cfg, wav, feat, taps=taps)
+    hcodec2.codec_decode(sd_cpu, cfg, ac, sc)
+    dt = time.perf_counter() - t0
+    return wav.numel() / dt, dt, taps, (ac, sc)
+
+
+def cpu_lm_generate(task, Bc=4, T=250):
+    """oracle port of LLM_SFT.generate (greedy) on the host: Bc sequences, the benchmarked prefix + 283 cached steps"""
+    from oracle import llama
+    n = cpu_threads()
+    sd = llama.make_lm_state_dict(LM_CFG, 7, 2.0)
+    g = torch.Generator().manual_seed(9)
+    mix = torch.randn(Bc, T, 768, generator=g)
+    enr = torch.randn(Bc, T, 768, generator=g) if task == "tse" else None
+    t0 = time.perf_counter()
+    llama.sft_generate(sd, LM_CFG, task, enr, mix, T)
+    dt = time.perf_counter() - t0
+    return dict(value=Bc * 283 / dt, unit="tokens/s", cores=n, host_cores=host_cores(), kind="port",
+                sample=f"{Bc} sequences x 283 tokens (prefix {503 if task == 'tse' else 252}, {dt:.1f} s), oracle port pinned against "
+                       "transformers.LlamaModel, torch CPU fp32")
+
+
+def run_reference(args, cfg):
+    """--impl reference: the reference's CPU path alone (oracle port), same metric / config, rank 0 only; the LM legs ride
+    in `secondary` like on the GPU arm."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import weights
+    sd = weights.make_h2_state_dict(cfg, 0)
+    clips = args.ref_clips
+    T = int(args.seconds * cfg["sampling_rate"])
+    T -= T % 3840
     g = torch.Generator().manual_seed(7)
     wav = 0.1 * torch.randn(clips, T, generator=g)
     f = torch.randn(clips, 768, T // 960, generator=g)
     feat = torch.sign(f) * f.abs() ** 0.3
-    t0 = time.perf_counter()
-    ac, sc = hcodec2.codec_encode(model_sd_cpu, cfg, wav, feat)
-    hcodec2.codec_decode(model_sd_cpu, cfg, ac, sc)
-    dt = time.perf_counter() - t0
-    return clips * T / dt, dt
-
-
-def run_reference(args, cfg):
-    """--impl reference: the CPU path alone, same metric / config (rank 0 only)."""
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
-    from oracle import weights
-    torch.manual_seed(0)
-    sd = weights.make_h2_state_dict(cfg, 0)
-    clips = args.ref_clips
     times = []
     for i in range(args.warmup + args.steps):
-        v, dt = cpu_baseline(sd, cfg, args.seconds, clips)
+        _, dt, _, _ = cpu_codec(sd, cfg, wav, feat)
         if i >= args.warmup:
             times.append(dt)
-    T = int(args.seconds * cfg["sampling_rate"])
     ms = 1e3 * sum(times) / len(times)
     value = clips * T / (ms / 1e3)
-    cores = _BEST_THREADS
+    n = cpu_threads()
+    sample = (f"{clips} clip(s) x {args.seconds:g} s per step, oracle port of the reference (pinned bit-exact against the "
+              f"reference modules), torch CPU fp32, {n} threads of {host_cores()} host cores")
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
                 config=dict(workload=f"HCodec-2.0 (48 kHz shipped config) {args.seconds:g} s clips, encode+RVQ+decode",
-                            batch_per_step=clips, samples_per_clip=T, cpu_threads=cores),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
-                                  sample=f"{clips} clip(s) x {args.seconds:g} s per step, oracle port of the reference "
-                                         f"(pinned bit-exact against the reference modules), torch CPU fp32"),
+                            batch_per_step=clips, samples_per_clip=T, cpu_threads=n, host_cores=host_cores()),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=n, host_cores=host_cores(), kind="port", sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    if args.workload == "all":
+        sec = {}
+        for name, task in (("lm_sr", "se"), ("lm_tse", "tse")):
+            c = cpu_lm_generate(task)
+            sec[name] = dict(metric=f"unise_{'sr' if task == 'se' else 'tse'}_arlm_generate_tokens_per_s", value=c["value"],
+                             unit="tokens/s", impl="reference", cpu_baseline=c)
+        line["secondary"] = sec
     print(json.dumps(line))
 
 
-def run_lm(args):
-    """Secondary line: UniSE SR AR-LM greedy generate (prefix 252 + 33 + 250 cached steps), B=32 per GPU.
-    tokens/s counts generated tokens (283 per sequence)."""
-    LM = dict(num_tasks=3, task_map=dict(se=0, tse=1, rtse=2), feats_dim=768,
-              llm_base_config=dict(cond_dim=80, global_size=4096, semantic_size=8192, hidden_size=512, num_layers=12,
-                                   num_attention_heads=8, dropout_p=0.1, max_position_embeddings=4096, label_smoothing=0.1))
-    B, T = 32, 250
-    if args.impl == "reference" and int(os.environ.get("RANK", "0")) != 0:
-        return
-    if args.impl == "reference":
-        from oracle import llama
-        sd = llama.make_lm_state_dict(LM, 7, 2.0)
-        Bc = 4
-        mix = torch.randn(Bc, T, 768)
-        torch.set_num_threads(min(32, os.cpu_count() or 1))
-        t0 = time.perf_counter()
-        llama.sft_generate(sd, LM, "se", None, mix, T)
-        dt = time.perf_counter() - t0
-        v = Bc * 283 / dt
-        print(json.dumps(dict(metric="unise_sr_arlm_generate_tokens_per_s", value=v, unit="tokens/s", n_gpus=args.gpus,
-                              steps=1, warmup=0, ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
-                              dtype="f32", data="synthetic", impl="reference",
-                              config=dict(workload="UniSE SR AR-LM greedy generate, prefix 252 + 283 cached steps", batch=Bc),
-                              cpu_baseline=dict(value=v, unit="tokens/s", cores=torch.get_num_threads(), kind="port",
-                                                sample=f"{Bc} sequences x 283 tokens, oracle port pinned against transformers.LlamaModel"),
-                              e2e=dict(value=v, unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)))
-        return
-    from unified_audio_b200 import ops
+# ------------------------------------------------------------------------------------------------ UniSE AR-LM
+def build_lm(dev):
     from unified_audio_b200.llm import LLM_SFT
-    from unified_audio_b200.parallel import gather_tokens
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:       # sequences are independent: B per rank (weak scaling), one all_gather of the generated ids
-        import torch.distributed as dist_
-        dist = dist_
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
-    m = LLM_SFT(num_tasks=3, task_map=LM["task_map"], feats_dim=768, llm_base_config=LM["llm_base_config"]).to(dev)
+    m = LLM_SFT(num_tasks=3, task_map=LM_CFG["task_map"], feats_dim=768, llm_base_config=LM_CFG["llm_base_config"]).to(dev)
     g = torch.Generator(device=dev).manual_seed(7)
-    with torch.no_grad():
+    with torch.no_grad():       # x2-gain weights so the logits are not near-uniform (SURVEY 8d)
         for n, p in m.named_parameters():
             if p.dim() >= 2 and "embedding" not in n:
                 p.copy_(torch.randn(p.shape, generator=g, device=dev) * (2.0 / p.shape[-1] ** 0.5))
@@ -250,104 +269,357 @@ def run_lm(args):
             else:
                 p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g, device=dev))
     m._w = None
-    mix_h = torch.randn(B, T, 768, generator=torch.Generator().manual_seed(100 + rank)).pin_memory()
-    mix = mix_h.to(dev)
+    return m
 
-    def step(src):
-        gi, si = m.generate("se", None, None, src, src, do_sample=False)
-        if dist is not None:
-            gather_tokens(torch.cat([gi, si], 1), world * B)
+
+def lm_decode_bytes(B, P, world):
+    """SURVEY 8(d) algorithmic bytes of one generation: per decode step the fp32-equivalent layer weights (4 B / parameter:
+    the packed fp16 hi/lo groups are the same size) + the active head slice + the fp32 KV read / write of every sequence."""
+    w_layers = 12 * (4 * 512 * 512 + 3 * 512 * 2048) * 4
+    head = 33 * 4096 * 512 * 4 + 250 * 8192 * 512 * 4
+    kv = sum(B * 2 * 12 * 512 * 4 * (P + i + 1) for i in range(283))
+    return world * (283 * w_layers + head) + kv        # B is already the whole-job batch; every rank streams its own replica
+
+
+def bench_lm_generate(args, ctx, m, task, B_local, total_batch=None, with_cpu=False, steps=None):
+    """UniSE AR-LM greedy generate (llm_sft.py:93-195): prefill (252 SR / 503 TSE positions) + 33 + 250 cached steps.
+    tokens/s counts generated tokens (283 per sequence).  `total_batch` (strong scaling): the job's batch is
+    fixed and split over the ranks; generate() walks it in chunks of <= 32 sequences."""
+    from unified_audio_b200 import ops
+    from unified_audio_b200.parallel import gather_tokens
+    T = 250
+    steps = steps or args.steps
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    if total_batch is not None:
+        from unified_audio_b200.parallel import shard_range
+        lo, hi = shard_range(total_batch, rank, world)
+        B_local = hi - lo
+    B_all = total_batch if total_batch is not None else B_local * world
+    g = torch.Generator().manual_seed(3000 + rank if task == "se" else 4001 + rank)
+    mix_h = torch.randn(B_local, T, 768, generator=g).pin_memory()
+    enr_h = torch.randn(B_local, T, 768, generator=g).pin_memory() if task == "tse" else None
+    mix = mix_h.to(dev)
+    enr = enr_h.to(dev) if enr_h is not None else None
+    gather_buf = {}
+
+    def step(src, esrc):
+        gi, si = m.generate(task, esrc, esrc, src, src, do_sample=False)
+        if ctx.dist is not None:
+            gather_tokens(torch.cat([gi, si], 1), B_all, buffers=gather_buf)
         return gi, si
 
-
-    def timed(fn):
-        if dist is not None:
-            dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(); e0.record()
-        for _ in range(args.steps):
-            fn()
-        e1.record(); torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t)
-
-    if args.workload == "lm_forward":
-        # teacher-forced UniSE LM forward (llm_sft.py:37-89): prefix 252 + 284 code tokens per sequence, logits over the
-        # 12291-entry vocabulary, loss + accuracy - the "AR-LM forward" of north_star.  Tensor-bound; every GEMM is a 3-term split.
-        gt = torch.Generator().manual_seed(7 + rank)
-        gids_h = torch.randint(0, 4096, (B, 32), generator=gt).pin_memory()
-        sids_h = torch.randint(0, 8192, (B, T), generator=gt).pin_memory()
-        gids, sids = gids_h.to(dev), sids_h.to(dev)
-        L = 2 + T + 32 + 1 + T + 1            # task + mix_sos + feats, then sos/global/sos/semantic (+ eos target)
-        fwd = lambda a, b_, c_: m("se", None, None, a, a, b_, c_)
-        for _ in range(max(args.warmup, 3)):
-            fwd(mix, gids, sids)
-        ops.launch_count_reset()
-        ms = timed(lambda: fwd(mix, gids, sids))
-        launches = ops.launch_count()
-
-        def e2e_fwd():
-            loss, acc = fwd(mix_h.to(dev, non_blocking=True), gids_h.to(dev, non_blocking=True), sids_h.to(dev, non_blocking=True))
-            loss.cpu(); acc.cpu()
-        ms_e2e = timed(e2e_fwd)
-        if rank == 0:
-            peaks = load_peaks()
-            per_tok = 12 * 2 * (4 * 512 * 512 + 3 * 512 * 2048)
-            flops = world * B * (L * per_tok + 12 * 4 * 512 * L * L / 2 + 2 * 768 * 512 * T + (T + 34) * 2 * 512 * 12291)
-            tf = flops / (ms * 1e-3) / 1e12
-            print(json.dumps(dict(
-                metric="unise_lm_forward_tokens_per_s", value=world * B * L / (ms * 1e-3), unit="tokens/s", n_gpus=world,
-                steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f16x3 split tensor-core (fp32-grade), f32 accumulate", data="synthetic",
-                config=dict(workload=f"UniSE LM teacher-forced forward, {B} sequences x {L} positions per GPU, logits + loss", batch=B * world,
-                            positions=L, parallelism=f"dp{world}"),
-                e2e=dict(value=world * B * L / (ms_e2e * 1e-3), unit="tokens/s", ms_per_step=ms_e2e,
-                         h2d_bytes_per_step=int(mix_h.numel() * 4 + gids_h.numel() * 8 + sids_h.numel() * 8) * world, d2h_bytes_per_step=8 * world),
-                gpu_launches=int(launches),
-                roofline=dict(bound="tensor", achieved=tf, peak=peaks["tf_sus"] * world, unit="TFLOP/s", frac=tf / (peaks["tf_sus"] * world),
-                              traffic=None, kernel="whole forward, algorithmic FLOPs (every GEMM and the attention issued 3x: ceiling 1/3)"))))
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-
-    for _ in range(max(args.warmup, 1)):
-        step(mix)
+    for _ in range(max(args.warmup, 2) if steps == args.steps else 1):
+        step(mix, enr)
     ops.launch_count_reset()
-    ms = timed(lambda: step(mix))
-    launches = ops.launch_count() // args.steps
+    ms = ctx.timed(lambda: step(mix, enr), steps)
+    launches = ops.launch_count() // steps
+    ids_h = torch.empty(B_local, 32 + T, dtype=torch.int64).pin_memory()
 
     def e2e_step():
-        gi, si = step(mix_h.to(dev, non_blocking=True))
-        gi.cpu(); si.cpu()
-    ms_e2e = timed(e2e_step)
-    B = B * world                       # whole-job totals from here on
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+        gi, si = step(mix_h.to(dev, non_blocking=True), enr_h.to(dev, non_blocking=True) if enr_h is not None else None)
+        ids_h[:, :32].copy_(gi, non_blocking=True)
+        ids_h[:, 32:].copy_(si, non_blocking=True)
+    ms_e2e = ctx.timed(e2e_step, steps)
+    P = 503 if task == "tse" else 252
     peaks = load_peaks()
-    # bytes per decode step: fp32 layer weights + head slice + fp32 KV read, summed over the 283 steps
-    w_bytes = 12 * (4 * 512 * 512 + 3 * 512 * 2048) * 4
-    kv = sum(B * 2 * 12 * 512 * 4 * (252 + i + 1) for i in range(283))
-    head = 33 * 4096 * 512 * 4 + 250 * 8192 * 512 * 4
-    total_bytes = world * (283 * w_bytes + head) + kv      # every rank streams its replica of the weights
-    gbs = total_bytes / (ms * 1e-3) / 1e9
-    print(json.dumps(dict(metric="unise_sr_arlm_generate_tokens_per_s", value=B * 283 / (ms * 1e-3), unit="tokens/s", n_gpus=world,
-                          steps=args.steps, warmup=max(args.warmup, 1), ms_per_step=ms, higher_is_better=True, scaling="weak",
-                          vs_baseline=None, dtype="f16x3 split tensor-core (fp32-grade), f32 accumulate / f32 KV cache", data="synthetic",
-                          config=dict(workload="UniSE SR AR-LM greedy generate (prefill 252 + 33 + 250 cached steps), batch=32 per GPU",
-                                      batch=B, semantic_length=T, parallelism=f"dp{world} (sequences sharded, one NCCL all_gather of ids)",
-                                      launches="decode steps replay one captured CUDA graph (62 kernels); gpu_launches counts eager launches + the capture"),
-                          e2e=dict(value=B * 283 / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=int(mix_h.numel() * 4) * world,
-                                   d2h_bytes_per_step=B * 282 * 8),
-                          gpu_launches=int(launches),
-                          roofline=dict(bound="hbm", achieved=gbs, peak=peaks["hbm"] * world, unit="GB/s", frac=gbs / (peaks["hbm"] * world),
-                                        traffic=None, kernel="decode step (lm_skinny<QKV|RESID|GATEUP|HEAD> + lm_decode_attn2), algorithmic bytes = 4 B/param packed "
-                                        "weights + head slice + fp32 KV read per step, whole generate incl. prefill"))))
-    if dist is not None:
-        dist.destroy_process_group()
+    gbs = lm_decode_bytes(B_all, P, world) / (ms * 1e-3) / 1e9
+    name = "sr" if task == "se" else "tse"
+    out = dict(metric=f"unise_{name}_arlm_generate_tokens_per_s", value=B_all * 283 / (ms * 1e-3), unit="tokens/s", n_gpus=world,
+               steps=steps, ms_per_step=ms, higher_is_better=True, scaling="strong" if total_batch is not None else "weak",
+               dtype="f16x3 split tensor-core (fp32-grade), f32 accumulate / f32 KV cache", data="synthetic",
+               config=dict(workload=f"UniSE {'SR' if task == 'se' else 'TSE (enrollment prefix)'} AR-LM greedy generate: prefill {P} + 33 + 250 cached "
+                                    f"steps, KV <= {P + 283}", batch=B_all, batch_per_gpu=B_local, semantic_length=T,
+                           parallelism=f"dp{world} (sequences sharded, one NCCL all_gather of ids)",
+                           launches="decode steps replay captured CUDA graphs (8 steps x 62 kernels each); gpu_launches counts the eager launches "
+                                    "(prefill, adapter) per generation"),
+               e2e=dict(value=B_all * 283 / (ms_e2e * 1e-3), unit="tokens/s", ms_per_step=ms_e2e,
+                        h2d_bytes_per_step=int(mix_h.numel() * 4 * (2 if task == "tse" else 1)) * world, d2h_bytes_per_step=B_all * 282 * 8),
+               gpu_launches=int(launches),
+               roofline=dict(bound="hbm", achieved=gbs, peak=peaks["hbm"] * world, unit="GB/s", frac=gbs / (peaks["hbm"] * world), traffic=None,
+                             kernel="decode step (lm_skinny<QKV|RESID|GATEUP|HEAD> + lm_decode_attn2): algorithmic bytes = 4 B/param layer weights + head "
+                                    "slice + fp32 KV read/write per step (SURVEY 8d), over the whole generate incl. prefill",
+                             peak_source=f"{peaks['src']} HBM copy bandwidth x {world} GPU(s)"))
+    if with_cpu and rank == 0:
+        out["cpu_baseline"] = cpu_lm_generate(task)
+    return out
+
+
+def bench_lm_forward(args, ctx, m):
+    """teacher-forced UniSE LM forward (llm_sft.py:37-89): prefix 252 + 284 code tokens per sequence, logits over the
+    12291-entry vocabulary, loss + accuracy - the "AR-LM forward" of north_star.  Tensor-bound; every GEMM is a 3-term split."""
+    from unified_audio_b200 import ops
+    B, T = 32, 250
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    mix_h = torch.randn(B, T, 768, generator=torch.Generator().manual_seed(100 + rank)).pin_memory()
+    mix = mix_h.to(dev)
+    gt = torch.Generator().manual_seed(7 + rank)
+    gids_h = torch.randint(0, 4096, (B, 32), generator=gt).pin_memory()
+    sids_h = torch.randint(0, 8192, (B, T), generator=gt).pin_memory()
+    gids, sids = gids_h.to(dev), sids_h.to(dev)
+    L = 2 + T + 32 + 1 + T + 1            # task + mix_sos + feats, then sos/global/sos/semantic (+ eos target)
+    fwd = lambda a, b_, c_: m("se", None, None, a, a, b_, c_)
+    for _ in range(max(args.warmup, 3)):
+        fwd(mix, gids, sids)
+    ops.launch_count_reset()
+    ms = ctx.timed(lambda: fwd(mix, gids, sids), args.steps)
+    launches = ops.launch_count() // args.steps
+
+    def e2e_fwd():
+        loss, acc = fwd(mix_h.to(dev, non_blocking=True), gids_h.to(dev, non_blocking=True), sids_h.to(dev, non_blocking=True))
+        loss.cpu(); acc.cpu()
+    ms_e2e = ctx.timed(e2e_fwd, args.steps)
+    peaks = load_peaks()
+    per_tok = 12 * 2 * (4 * 512 * 512 + 3 * 512 * 2048)
+    flops = world * B * (L * per_tok + 12 * 4 * 512 * L * L / 2 + 2 * 768 * 512 * T + (T + 34) * 2 * 512 * 12291)
+    tf = flops / (ms * 1e-3) / 1e12
+    return dict(
+        metric="unise_lm_forward_tokens_per_s", value=world * B * L / (ms * 1e-3), unit="tokens/s", n_gpus=world,
+        steps=args.steps, ms_per_step=ms, higher_is_better=True, scaling="weak",
+        dtype="f16x3 split tensor-core (fp32-grade), f32 accumulate", data="synthetic",
+        config=dict(workload=f"UniSE LM teacher-forced forward, {B} sequences x {L} positions per GPU, logits + loss", batch=B * world,
+                    positions=L, parallelism=f"dp{world}"),
+        e2e=dict(value=world * B * L / (ms_e2e * 1e-3), unit="tokens/s", ms_per_step=ms_e2e,
+                 h2d_bytes_per_step=int(mix_h.numel() * 4 + gids_h.numel() * 8 + sids_h.numel() * 8) * world, d2h_bytes_per_step=8 * world),
+        gpu_launches=int(launches),
+        roofline=dict(bound="tensor", achieved=tf, peak=peaks["tf_sus"] * world, unit="TFLOP/s", frac=tf / (peaks["tf_sus"] * world),
+                      traffic=None, kernel="whole forward, algorithmic FLOPs (every GEMM and the attention issued 3x: ceiling 1/3)"))
+
+
+# ------------------------------------------------------------------------------------------------ H-Codec-2.0
+def build_codec(cfg, dev, precision):
+    from unified_audio_b200.codec import Codec
+    model = Codec(cfg["encoder_config"], cfg["decoder_config"], cfg["quantizer_config"],
+                  cfg["semantic_encoder_config"], cfg["semantic_decoder_config"], precision=precision).to(dev)
+    random_init_(model, 1234)
+    return model
+
+
+def synth_batch(cfg, B, seconds, seed):
+    T = int(seconds * cfg["sampling_rate"])
+    T -= T % 3840
+    g = torch.Generator().manual_seed(seed)
+    wav_h = (0.1 * torch.randn(B, T, generator=g)).pin_memory()
+    f = torch.randn(B, 768, T // 960, generator=g)
+    feat_h = (torch.sign(f) * f.abs() ** 0.3).pin_memory()
+    return wav_h, feat_h, T
+
+
+def bench_codec_strong(args, ctx, model, cfg, total):
+    """BASELINE configs[4] as written: `total` clips sharded over the ranks (strong scaling); each rank walks its shard in chunks
+    of <= 64 clips through the captured round trip; one token all-gather per step."""
+    from unified_audio_b200.parallel import gather_tokens, shard_range
+    lo, hi = shard_range(total, ctx.rank, ctx.world)
+    n_local = hi - lo
+    chunk = min(64, n_local)
+    wav_h, feat_h, T = synth_batch(cfg, chunk, args.seconds, 5000 + ctx.rank)
+    wav_d, feat_d = wav_h.to(ctx.dev), feat_h.to(ctx.dev)
+    graphed = model.graphed("roundtrip", wav_d, feat_d)
+    n_chunks = -(-n_local // chunk)
+    toks = torch.zeros(n_local, 2, 16, T // 3840, dtype=torch.int64, device=ctx.dev)
+    gbuf = {}
+
+    def step():
+        for c in range(n_chunks):
+            ac, sc, rec = graphed()
+            n = min(chunk, n_local - c * chunk)
+            toks[c * chunk:c * chunk + n, 0].copy_(ac[:n])
+            toks[c * chunk:c * chunk + n, 1].copy_(sc[:n])
+        if ctx.dist is not None:
+            gather_tokens(toks, total, buffers=gbuf)
+    step()
+    ms = ctx.timed(step, max(2, min(args.steps, 3)))
+    return dict(metric=METRIC, value=total * T / (ms * 1e-3), unit=UNIT, n_gpus=ctx.world, ms_per_step=ms, scaling="strong",
+                config=dict(workload=f"HCodec-2.0 batch={total} x {args.seconds:g} s (BASELINE configs[4]) sharded over {ctx.world} GPU(s)",
+                            clips_per_gpu=n_local, chunk=chunk, chunks_per_step=n_chunks),
+                note="last chunk of a shard that is not a multiple of the chunk size is computed in full and trimmed" if n_local % chunk else None)
+
+
+def run_codec(args, cfg, ctx, collect_secondary):
+    from unified_audio_b200 import ops
+    from unified_audio_b200.parallel import gather_tokens
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    peaks = load_peaks()
+    model = build_codec(cfg, dev, args.precision)
+    B = args.batch
+    wav_h, feat_h, T = synth_batch(cfg, B, args.seconds, 2000 + rank)
+    F_ = T // 960
+    wav_d, feat_d = wav_h.to(dev), feat_h.to(dev)
+
+    # the public fixed-shape entry point: encode -> decode captured once in a CUDA graph (Codec.graphed), replayed per step
+    graphed = None
+    if not args.no_graph:
+        try:
+            graphed = model.graphed("roundtrip", wav_d, feat_d)
+        except Exception as e:      # same kernels either way: fall back to launching them one by one
+            print(f"[bench] CUDA-graph capture failed ({e!r}); launching kernel by kernel", file=sys.stderr)
+            torch.cuda.synchronize()
+    gbuf = {}
+    tok_stack = torch.zeros(B, 2, 16, T // 3840, dtype=torch.int64, device=dev)
+
+    def step_device():
+        if graphed is not None:
+            ac, sc, rec = graphed()                      # static inputs already hold this rank's batch (HBM-resident)
+        else:
+            ac, sc = model.encode(wav_d, feat_d)
+            rec = model.decode(ac, sc)
+        if ctx.dist is not None:   # the path's single exchange: gather the int64 tokens (SURVEY 8e)
+            tok_stack[:, 0].copy_(ac)
+            tok_stack[:, 1].copy_(sc)
+            gather_tokens(tok_stack, world * B, buffers=gbuf)
+        return ac, sc, rec
+
+    codes_h = torch.empty(2, B, 16, T // 3840, dtype=torch.int64).pin_memory()
+    rec_h = torch.empty(B, T).pin_memory()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step_e2e(split=False):
+        if split:
+            ev[0].record()
+        if graphed is not None:
+            for dst, src in zip(graphed.inputs, (wav_h, feat_h)):      # pinned host -> static device inputs (H2D inside the timed region)
+                dst.copy_(src, non_blocking=True)
+            if split:
+                ev[1].record()
+            ac, sc, rec = graphed()
+        else:
+            w = wav_h.to(dev, non_blocking=True)
+            ft = feat_h.to(dev, non_blocking=True)
+            if split:
+                ev[1].record()
+            ac, sc = model.encode(w, ft)
+            rec = model.decode(ac, sc)
+        if split:
+            ev[2].record()
+        codes_h[0].copy_(ac, non_blocking=True)
+        codes_h[1].copy_(sc, non_blocking=True)
+        rec_h.copy_(rec, non_blocking=True)
+        if split:
+            ev[3].record()
+        return rec
+
+    if args.quick:
+        for _ in range(args.warmup):
+            step_device()
+        ms = ctx.timed(step_device, args.steps)
+        if rank == 0:
+            print(json.dumps(dict(quick=True, ms_per_step=ms, value=world * B * T / (ms * 1e-3))))
+        return None
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(ctx.local)
+    if rank == 0:
+        sampler.start()
+    ops.launch_count_reset()
+    ms = ctx.timed(step_device, args.steps)
+    launches = ops.launch_count() + (graphed.launches_per_replay * args.steps if graphed is not None else 0)
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = ctx.timed(step_e2e, args.steps)
+    torch.cuda.synchronize()
+    step_e2e(split=True)
+    torch.cuda.synchronize()
+    e2e_split = dict(h2d_ms=ev[0].elapsed_time(ev[1]), compute_ms=ev[1].elapsed_time(ev[2]), d2h_ms=ev[2].elapsed_time(ev[3]),
+                     note="one extra step, serial on the launching stream (no overlap between copies and kernels)")
+
+    # ---- roofline of the dominant kernel: the ConvNeXt pointwise GEMM (tcgen05), timed alone
+    M, C, I = B * F_, 1536, 4608
+    blk = model._prepare()["enc"]["convnext"][0]
+    t1 = model._planes("cnx_t1", (M, C), model.policy["convnext"])
+    hid = model._planes("cnx_hid", (M, I), model.policy["convnext"])
+    reps = 10
+    run1 = lambda: model._linear(t1, blk["w1"], I, M, C, bias=blk["b1"], act=ops.ACT_GELU, out_planes=hid, out_planes_map=(I, M, 0))
+    for _ in range(3):
+        run1()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        run1()
+    e1.record()
+    torch.cuda.synchronize()
+    gemm_ms = e0.elapsed_time(e1) / reps
+    gemm_tf = 2.0 * M * I * C / (gemm_ms * 1e-3) / 1e12
+
+    samples = world * B * T
+    value = samples / (ms * 1e-3)
+    path_tf = world * B * F_ * FLOP_PER_FRAME / (ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    line = dict(
+        metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+        ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16x3/f16 tensor-core, f32 accumulate",
+        data="synthetic",
+        config=dict(workload=f"HCodec-2.0 batch={B} x {args.seconds:g} s (48 kHz shipped config, {T} samples/clip) encode+RVQ+decode",
+                    batch_per_gpu=B, samples_per_clip=T, tokens_per_stream=T // 3840, precision_policy=args.precision,
+                    l2="working set per step (~3 GB activations + 4.6 GB weights) exceeds the 126 MB L2; no flush needed",
+                    parallelism=f"dp{world} (clips sharded, one NCCL all_gather_into_tensor of tokens)",
+                    launch="one CUDA graph replay per step (Codec.graphed('roundtrip')); gpu_launches = library kernels in the "
+                           "graph x steps" if graphed is not None else "kernel by kernel"),
+        e2e=dict(value=samples / (ms_e2e * 1e-3), unit=UNIT, ms_per_step=ms_e2e,
+                 h2d_bytes_per_step=int(wav_h.numel() * 4 + feat_h.numel() * 4) * world,
+                 d2h_bytes_per_step=int(codes_h.numel() * 8 + rec_h.numel() * 4) * world, split=e2e_split),
+        gpu_launches=int(launches),
+        clocks=clocks,
+        roofline=dict(bound="tensor", achieved=gemm_tf, peak=peaks["tf_burst"], unit="TFLOP/s", frac=gemm_tf / peaks["tf_burst"],
+                      traffic=traffic, kernel=f"{ops.gemm_kernel_name(M, I, False)} ConvNeXt pwconv1 [{M}x{I}x{C}] fp16 + GELU epilogue, timed alone on rank 0",
+                      peak_source=f"{peaks['src']} dense bf16 burst (fp16 shares the pipe), one GPU",
+                      path_algorithmic_tflops=path_tf, path_algorithmic_tflops_per_gpu=path_tf / world,
+                      path_frac_of_sustained=path_tf / (peaks["tf_sus"] * world)),
+    )
+    line["cpu_baseline"] = None                  # timed on rank 0 at N = 1 only (the N > 1 lines carry the key, empty)
+    line["parity"] = None
+    if not args.no_cpu_baseline and world == 1:
+        # clip 0 of the timed batch on the reference's CPU path: the CPU baseline AND the parity check of this very run
+        from oracle import hcodec2
+        from oracle.parity import audit_codes
+        sd_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        v, dt, otaps, (oa, os_) = cpu_codec(sd_cpu, cfg, wav_h[:1].clone(), feat_h[:1].clone(), want_codes=True)
+        n = cpu_threads()
+        line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=n, host_cores=host_cores(), kind="port",
+                                    sample=f"1 clip x {args.seconds:g} s encode+RVQ+decode ({dt:.1f} s), oracle port of "
+                                           f"the reference's PyTorch CPU path, same weights, {n} threads")
+        gtaps = {}
+        ac, sc = model.encode(wav_d, feat_d, taps=gtaps)
+        rec = model.decode(oa.to(dev), os_.to(dev))
+        ref = hcodec2.codec_decode(sd_cpu, cfg, oa, os_)
+        rows = lambda t: t[:1].float().cpu().transpose(1, 2).reshape(-1, t.shape[1])
+        relf = lambda a, b: float((a.double().cpu() - b.double()).abs().max() / b.double().abs().max())
+        par = dict(sample="clip 0 of the timed batch vs the oracle (same weights, same run)",
+                   emb_rel=relf(gtaps["enc.out"][:1], otaps["enc.out"]), sem_rel=relf(gtaps["sem.out"][:1], otaps["sem.out"]),
+                   wav_rel=relf(rec, ref))
+        for tag, got, want, key, q in (("acoustic", ac[:1], oa, "enc.out", "quantizer"), ("semantic", sc[:1], os_, "sem.out", "semantic_quantizer")):
+            a = audit_codes(got, want, rows(gtaps[key]), rows(otaps[key]), hcodec2._codebooks(sd_cpu, q))
+            par[tag] = {k: a[k] for k in ("tokens", "tokens_differing", "index_match_rate", "worst_gap", "worst_reach", "explained")}
+        par["ok"] = bool(par["emb_rel"] < 1e-3 and par["sem_rel"] < 1e-3 and par["wav_rel"] < 1e-3 and par["acoustic"]["explained"]
+                         and par["semantic"]["explained"])
+        line["parity"] = par
+    sec = None
+    if collect_secondary:
+        sec = {}
+        try:
+            sec["codec_b256_strong"] = bench_codec_strong(args, ctx, model, cfg, 256)
+        except Exception as e:
+            sec["codec_b256_strong"] = dict(error=repr(e))
+        if world == 1 and args.precision != "accurate":
+            try:        # fp32-grade policy (every GEMM a 3-term split) beside the default
+                del graphed
+                model._ws = {}
+                torch.cuda.empty_cache()
+                macc = build_codec(cfg, dev, "accurate")
+                gacc = macc.graphed("roundtrip", wav_d, feat_d)
+                gacc()
+                ms_acc = ctx.timed(lambda: gacc(), 3)
+                sec["codec_accurate_policy"] = dict(metric=METRIC, value=B * T / (ms_acc * 1e-3), unit=UNIT, ms_per_step=ms_acc,
+                                                    config=dict(precision_policy="accurate", batch_per_gpu=B))
+                del gacc, macc
+            except Exception as e:
+                sec["codec_accurate_policy"] = dict(error=repr(e))
+    del model
+    torch.cuda.empty_cache()
+    return line, sec
 
 
 def bicodec_flops_per_clip(cfg, T):
@@ -513,182 +785,60 @@ def main():
     ap.add_argument("--precision", default="mixed")
     ap.add_argument("--ref-clips", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="codec", choices=["codec", "lm", "lm_forward", "bicodec"],
-                    help="codec = BASELINE configs[1] (default, the driver's line); lm = UniSE SR AR-LM generate (configs[2]); "
-                         "bicodec = BiCodec detokenize, the decoder UniSE feeds the LM tokens to")
+    ap.add_argument("--workload", default="all", choices=["all", "codec", "lm", "lm_tse", "lm_forward", "bicodec"],
+                    help="all (default, the driver's line) = the codec line (BASELINE configs[1]) with the UniSE AR-LM legs (configs[2], [3], "
+                         "[4]) under `secondary`; codec / lm / lm_tse / lm_forward / bicodec = that line alone")
     ap.add_argument("--quick", action="store_true", help="profiling aid: W warm-up + K steps only, no e2e/roofline/cpu legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     cfg = H2_FULL
-    if args.workload in ("lm", "lm_forward"):
-        return run_lm(args)
     if args.workload == "bicodec":
         return run_bicodec(args)
     if args.impl == "reference":
+        if args.workload in ("lm", "lm_tse"):
+            if int(os.environ.get("RANK", "0")) == 0:
+                c = cpu_lm_generate("tse" if args.workload == "lm_tse" else "se")
+                print(json.dumps(dict(metric="unise_arlm_generate_tokens_per_s", value=c["value"], unit="tokens/s", impl="reference",
+                                      n_gpus=args.gpus, higher_is_better=True, cpu_baseline=c,
+                                      e2e=dict(value=c["value"], unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+            return
         return run_reference(args, cfg)
-
-    from unified_audio_b200 import ops
-    from unified_audio_b200.codec import Codec
-    from unified_audio_b200.parallel import gather_tokens
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_
-        dist = dist_
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
-    peaks = load_peaks()
-
-    model = Codec(cfg["encoder_config"], cfg["decoder_config"], cfg["quantizer_config"],
-                  cfg["semantic_encoder_config"], cfg["semantic_decoder_config"], precision=args.precision).to(dev)
-    random_init_(model, 1234)
-    B, T = args.batch, int(args.seconds * cfg["sampling_rate"])
-    T -= T % 3840
-    F_ = T // 960
-    g = torch.Generator().manual_seed(2000 + rank)
-    wav_h = (0.1 * torch.randn(B, T, generator=g)).pin_memory()
-    f = torch.randn(B, 768, F_, generator=g)
-    feat_h = (torch.sign(f) * f.abs() ** 0.3).pin_memory()
-    wav_d, feat_d = wav_h.to(dev), feat_h.to(dev)
-
-    # the public fixed-shape entry point: encode -> decode captured once in a CUDA graph (Codec.graphed), replayed per step
-    graphed = None
-    if not args.no_graph:
-        try:
-            graphed = model.graphed("roundtrip", wav_d, feat_d)
-        except Exception as e:      # same kernels either way: fall back to launching them one by one
-            print(f"[bench] CUDA-graph capture failed ({e!r}); launching kernel by kernel", file=sys.stderr)
-            torch.cuda.synchronize()
-
-    def step_device():
-        if graphed is not None:
-            ac, sc, rec = graphed()                      # static inputs already hold this rank's batch (HBM-resident)
+    ctx = Ctx()
+    if args.workload in ("lm", "lm_tse", "lm_forward"):
+        m = build_lm(ctx.dev)
+        if args.workload == "lm_forward":
+            out = bench_lm_forward(args, ctx, m)
         else:
-            ac, sc = model.encode(wav_d, feat_d)
-            rec = model.decode(ac, sc)
-        if dist is not None:   # the path's single exchange: gather the int64 tokens
-            gather_tokens(torch.stack([ac, sc], 1), world * B)
-        return ac, sc, rec
-
-    codes_h = torch.empty(2, B, 16, T // 3840, dtype=torch.int64).pin_memory()
-    rec_h = torch.empty(B, T).pin_memory()
-
-    def step_e2e():
-        if graphed is not None:
-            ac, sc, rec = graphed(wav_h, feat_h)         # pinned host -> static device inputs (H2D inside the timed region)
-        else:
-            w = wav_h.to(dev, non_blocking=True)
-            ft = feat_h.to(dev, non_blocking=True)
-            ac, sc = model.encode(w, ft)
-            rec = model.decode(ac, sc)
-        codes_h[0].copy_(ac, non_blocking=True)
-        codes_h[1].copy_(sc, non_blocking=True)
-        rec_h.copy_(rec, non_blocking=True)
-        return rec
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-        barrier()
-        ev[0].record()
-        for i in range(steps):
-            fn()
-            ev[i + 1].record()
-        barrier()
-        total_ms = ev[0].elapsed_time(ev[-1])
-        if dist is not None:
-            t = torch.tensor([total_ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t)
-        return total_ms / steps
-
-    if args.quick:
-        for _ in range(args.warmup):
-            step_device()
-        ms = timed(step_device, args.steps)
-        if rank == 0:
-            print(json.dumps(dict(quick=True, ms_per_step=ms, value=world * B * T / (ms * 1e-3))))
+            task = "tse" if args.workload == "lm_tse" else "se"
+            out = bench_lm_generate(args, ctx, m, task, 16 if task == "tse" else 32, with_cpu=ctx.world == 1 and not args.no_cpu_baseline)
+        out.update(warmup=max(args.warmup, 2), vs_baseline=None)
+        if ctx.rank == 0:
+            print(json.dumps(out))
+        ctx.close()
         return
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ops.launch_count_reset()
-    ms = timed(step_device, args.steps)
-    launches = ops.launch_count() + (graphed.launches_per_replay * args.steps if graphed is not None else 0)
-    clocks = sampler.stop() if rank == 0 else None
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
-
-    # ---- roofline of the dominant kernel: the ConvNeXt pointwise GEMM (tcgen05), timed alone
-    M, C, I = B * F_, 1536, 4608
-    blk = model._prepare()["enc"]["convnext"][0]
-    t1 = model._planes("cnx_t1", (M, C), model.policy["convnext"])
-    hid = model._planes("cnx_hid", (M, I), model.policy["convnext"])
-    reps = 10
-    for _ in range(3):
-        model._linear(t1, blk["w1"], I, M, C, bias=blk["b1"], act=ops.ACT_GELU, out_planes=hid, out_planes_map=(I, M, 0))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(reps):
-        model._linear(t1, blk["w1"], I, M, C, bias=blk["b1"], act=ops.ACT_GELU, out_planes=hid, out_planes_map=(I, M, 0))
-    e1.record()
-    torch.cuda.synchronize()
-    gemm_ms = e0.elapsed_time(e1) / reps
-    gemm_tf = 2.0 * M * I * C / (gemm_ms * 1e-3) / 1e12
-
-    if rank != 0:
+    res = run_codec(args, cfg, ctx, collect_secondary=args.workload == "all" and not args.quick)
+    if res is None:
+        ctx.close()
         return
-    samples = world * B * T
-    value = samples / (ms * 1e-3)
-    path_tf = world * B * F_ * FLOP_PER_FRAME / (ms * 1e-3) / 1e12
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    line = dict(
-        metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-        ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16x3/f16 tensor-core, f32 accumulate",
-        data="synthetic",
-        config=dict(workload="HCodec-2.0 batch=64 x 10 s (48 kHz shipped config, 480000 samples/clip) encode+RVQ+decode",
-                    batch_per_gpu=B, samples_per_clip=T, tokens_per_stream=T // 3840, precision_policy=args.precision,
-                    l2="working set per step (~3 GB activations + 4.6 GB weights) exceeds the 126 MB L2; no flush needed",
-                    parallelism=f"dp{world} (clips sharded, one NCCL all_gather of tokens)",
-                    launch="one CUDA graph replay per step (Codec.graphed('roundtrip')); gpu_launches = library kernels in the "
-                           "graph x steps" if graphed is not None else "kernel by kernel"),
-        e2e=dict(value=samples / (ms_e2e * 1e-3), unit=UNIT, ms_per_step=ms_e2e,
-                 h2d_bytes_per_step=int(wav_h.numel() * 4 + feat_h.numel() * 4),
-                 d2h_bytes_per_step=int(codes_h.numel() * 8 + rec_h.numel() * 4)),
-        gpu_launches=int(launches),
-        clocks=clocks,
-        roofline=dict(bound="tensor", achieved=gemm_tf, peak=peaks["tf_burst"], unit="TFLOP/s", frac=gemm_tf / peaks["tf_burst"],
-                      traffic=traffic, kernel="gemm_tc2_kernel<256,1,6> (cta_group::2) ConvNeXt pwconv1 [32000x4608x1536] fp16 + GELU epilogue, timed alone",
-                      peak_source=f"{peaks['src']} dense bf16 burst (fp16 shares the pipe)",
-                      path_algorithmic_tflops=path_tf, path_frac_of_sustained=path_tf / peaks["tf_sus"]),
-    )
-    line["cpu_baseline"] = None                  # timed on rank 0 at N = 1 only (the N > 1 lines carry the key, empty)
-    if not args.no_cpu_baseline and world == 1:
-        sd_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-        v, dt = cpu_baseline(sd_cpu, cfg, args.seconds, 1)
-        line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=_BEST_THREADS, kind="port",
-                                    sample=f"1 clip x {args.seconds:g} s encode+RVQ+decode ({dt:.1f} s), oracle port of "
-                                           "the reference's PyTorch CPU path, same weights")
-    print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    line, sec = res
+    if args.workload == "all":
+        # the AR-LM half of BASELINE.json's metric in the same invocation: SR B=32 (configs[2]), TSE B=16 (configs[3]) per GPU,
+        # the batch-256 sweep (configs[4]) and the teacher-forced forward
+        m = build_lm(ctx.dev)
+        with_cpu = ctx.world == 1 and not args.no_cpu_baseline
+        for name, fn in (("lm_sr", lambda: bench_lm_generate(args, ctx, m, "se", 32, with_cpu=with_cpu)),
+                         ("lm_tse", lambda: bench_lm_generate(args, ctx, m, "tse", 16, with_cpu=with_cpu)),
+                         ("lm_sr_b256_strong", lambda: bench_lm_generate(args, ctx, m, "se", None, total_batch=256, steps=2)),
+                         ("lm_forward", lambda: bench_lm_forward(args, ctx, m))):
+            try:
+                sec[name] = fn()
+            except Exception as e:          # a secondary leg never takes the headline line down
+                sec[name] = dict(error=repr(e))
+                torch.cuda.synchronize()
+        line["secondary"] = sec
+    if ctx.rank == 0:
+        print(json.dumps(line))
+    ctx.close()
 
 
 if __name__ == "__main__":

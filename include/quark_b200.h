@@ -92,6 +92,9 @@ typedef struct {
 
 /* tcgen05 / TMA / TMEM persistent GEMM (the product path). */
 int qb_gemm(const qb_gemm_desc* d, void* stream);
+/* Name of the kernel variant qb_gemm runs for this shape (m_per_batch output rows per batch, n columns, split != 0 for the
+ * 3-term mode) - static string, used by bench.py's roofline label. */
+const char* qb_gemm_kernel_name(int64_t m_per_batch, int64_t n, int32_t split);
 /* Plain SIMT evaluation of the same descriptor - a device-side cross-check used by tests only. */
 int qb_gemm_simt(const qb_gemm_desc* d, void* stream);
 
@@ -264,6 +267,19 @@ int qb_lm_decode_layer_tc(float* x, int64_t B, int32_t hidden, int32_t heads, in
 int qb_lm_head_argmax_tc(const float* x, int64_t B, int32_t hidden, const qb_half* w_head, const int32_t* range,
                          int32_t max_cols, const float* embedding, float* x_next, int64_t* out_ids, int32_t out_stride,
                          int32_t* pos, int32_t* slot, float* part_val, int32_t* part_idx, void* stream);
+
+/* Sampled decoding step (CustomLlamaModel.sample_logits, QuarkAudio-UniSE/model/llm/llm.py:253-289, as called from
+ * llm_sft.py:155-161,184-190 with the reference defaults temperature 0.8, top_k 50, top_p 0.95, do_sample=True):
+ * as qb_lm_head_argmax_tc, but the head also writes the range logits to `logits` [B][max_cols] and the token is drawn as
+ * top-k (ties at the k-th value kept) -> top-p over the survivors' softmax (sorted descending; the first token always stays)
+ * -> / temperature -> softmax -> inverse-CDF draw over the kept tokens in descending-logit order at
+ * u = Philox4x32-10(key = {seed[0], seed[1]}, counter = {step (= slot[0]), row, seed[2], 0}).x >> 8) * 2^-24.
+ * seed: device uint32[4] {seed_lo, seed_hi, call_counter, 0}; debug: optional device float [B][4] = {u, survivors after
+ * top-k, kept after top-p, sum of the kept exp((l - max)/T)} or NULL.  1 <= top_k <= 1024; 0 < temperature <= 1. */
+int qb_lm_head_sample_tc(const float* x, int64_t B, int32_t hidden, const qb_half* w_head, const int32_t* range,
+                         int32_t max_cols, const float* embedding, float* x_next, int64_t* out_ids, int32_t out_stride,
+                         int32_t* pos, int32_t* slot, float* part_val, int32_t* part_idx, float* logits,
+                         float temperature, int32_t top_k, float top_p, const uint32_t* seed, float* debug, void* stream);
 
 #ifdef __cplusplus
 }

@@ -195,3 +195,58 @@ def sft_generate(sd, cfg, task_name, enroll_feats, mix_feats, semantic_length, g
     if return_margins:
         return global_ids, semantic_ids, torch.stack(margins, 1)
     return global_ids, semantic_ids
+
+
+# --------------------------------------------------------------------------- sampled decoding (llm.py:253-289)
+def sample_filter(logits, temperature=0.8, top_k=50, top_p=0.95):
+    """The reference's sample_logits up to (not including) the multinomial draw: returns the final probabilities
+    [B, V'] (zeros where a token was filtered out).  Steps, in the reference's order: top-k by threshold value
+    (`logits < topk[-1]` removed, ties at the k-th value stay) -> top-p on the descending sort of the survivors
+    (a token goes when the cumulative softmax BEFORE it exceeds top_p; the first always stays) -> / temperature ->
+    softmax."""
+    logits = logits.clone().float()
+    if top_k > 0:
+        kth = torch.topk(logits, top_k)[0][..., -1, None]
+        logits[logits < kth] = float("-inf")
+    if top_p < 1.0:
+        sorted_logits, sorted_indices = torch.sort(logits, descending=True)
+        cum = torch.cumsum(F.softmax(sorted_logits, dim=-1), dim=-1)
+        rem = cum > top_p
+        rem[..., 1:] = rem[..., :-1].clone()
+        rem[..., 0] = 0
+        logits[rem.scatter(-1, sorted_indices, rem)] = float("-inf")
+    assert 0 < temperature <= 1.0
+    return F.softmax(logits / temperature, dim=-1)
+
+
+def philox4x32_10(key, counter):
+    """Philox-4x32 with 10 rounds (Salmon et al. 2011): key (k0, k1), counter (c0, c1, c2, c3) -> 4 uint32."""
+    M0, M1, W0, W1, mask = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+    k0, k1 = key
+    c0, c1, c2, c3 = counter
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & mask, p1 & mask, ((p0 >> 32) ^ c3 ^ k1) & mask, p0 & mask
+        k0, k1 = (k0 + W0) & mask, (k1 + W1) & mask
+    return c0, c1, c2, c3
+
+
+def sample_uniform(seed, call, step, row):
+    """The uniform in [0,1) the device sampler uses for (generate call chunk, decode step, batch row):
+    24 high bits of Philox4x32-10(key = seed split lo/hi, counter = {step, row, call, 0}).x (include/quark_b200.h)."""
+    r = philox4x32_10((seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF), (step, row, call, 0))[0]
+    return (r >> 8) / 16777216.0
+
+
+def inverse_cdf_pick(probs_row, u):
+    """Inverse-CDF draw over the kept tokens in descending-probability order (ties: ascending id), the order the device
+    sampler defines.  Returns (token, distance of u*S to the nearest CDF boundary / S)."""
+    idx = torch.nonzero(probs_row > 0).flatten()
+    p = probs_row[idx].double()
+    order = sorted(range(len(idx)), key=lambda i: (-float(p[i]), int(idx[i])))
+    cdf = torch.cumsum(p[order], 0)
+    t = u * float(cdf[-1])
+    k = int(torch.searchsorted(cdf, torch.tensor(t, dtype=torch.float64), right=True))
+    k = min(k, len(order) - 1)
+    near = float((cdf - t).abs().min() / cdf[-1])
+    return int(idx[order[k]]), near

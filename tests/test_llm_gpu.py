@@ -122,3 +122,88 @@ def test_lm_decode_kernels_agree(lib, B):
     e_tc, e_simt, e_x = rel(outs["tc"], ref[:, 40:]), rel(outs["simt"], ref[:, 40:]), rel(outs["tc"], outs["simt"])
     print(f"B={B}: decode rel vs oracle tc {e_tc:.2e} simt {e_simt:.2e}; tc vs simt {e_x:.2e}")
     assert e_tc < TOL and e_simt < TOL and e_x < 1e-4
+
+
+def test_lm_sampled_generate_vs_oracle(lib):
+    """do_sample=True with the reference's default arguments (temperature 0.8, top_k 50, top_p 0.95; llm_sft.py:93-107).
+    The device sampler's tokens are replayed on the oracle along the device's own token path: at every step the token must
+    lie in the reference's filtered support (top-k -> top-p restated verbatim in oracle.llama.sample_filter) and must be the
+    inverse-CDF pick at the same Philox uniform, except where the uniform lands within 1e-5 of a CDF boundary."""
+    from oracle import llama
+    cfg = llama.LM_FULL
+    m, sd = build(cfg, 7, 2.0)
+    g = torch.Generator().manual_seed(21)
+    B, T, seed = 3, 12, 123456789012345
+    mix = torch.randn(B, T, 768, generator=g)
+    for use_graph in (False, True):
+        gg, ss = m.generate("se", None, None, mix.cuda(), mix.cuda(), use_cuda_graph=use_graph, seed=seed)   # do_sample default True
+        torch.cuda.synchronize()
+        gg, ss = gg.cpu(), ss.cpu()
+        assert gg.shape == (B, 32) and ss.shape == (B, T)
+        assert int(gg.min()) >= 0 and int(gg.max()) < 4096 and int(ss.min()) >= 0 and int(ss.max()) < 8192
+        if use_graph:
+            assert torch.equal(gg, first[0]) and torch.equal(ss, first[1]), "graph replay must reproduce the eager sampled tokens"
+        first = (gg, ss)
+    # replay on the oracle (teacher-forced along the device's tokens)
+    goff, soff = 3, 3 + 4096
+    st = m._gen_state[next(iter(m._gen_state))]
+    all_ids = st["out_ids"].cpu()                                   # [B, 33 + T] raw ids incl. the discarded 33rd global step
+    hs, cache = llama.llm_forward(sd, cfg, llama._prefix(sd, cfg, "se", None, mix))
+    ids = torch.zeros(B, 1, dtype=torch.long)
+    n_in_support = n_same = n_close = 0
+    total = 33 + T
+    for step in range(total):
+        if step == 33:
+            ids = torch.ones(B, 1, dtype=torch.long)
+        lo, hi = (goff, goff + 4096) if step < 33 else (soff, soff + 8192)
+        h, cache = llama.llm_forward(sd, cfg, sd["codec_embedding.weight"][ids], cache)
+        logits = torch.nn.functional.linear(h[:, 0], sd["output_head.weight"])[:, lo:hi]
+        probs = llama.sample_filter(logits, 0.8, 50, 0.95)
+        for b in range(B):
+            tok = int(all_ids[b, step]) - lo
+            assert 0 <= tok < hi - lo
+            n_in_support += int(probs[b, tok] > 0)
+            want, near = llama.inverse_cdf_pick(probs[b], llama.sample_uniform(seed, 0, step, b))
+            if want == tok:
+                n_same += 1
+            elif near < 1e-4 or float(probs[b, tok]) < 1e-4:
+                n_close += 1            # uniform on a CDF boundary / support edge at the float tolerance
+            else:
+                raise AssertionError(f"step {step} row {b}: device token {tok} (p={float(probs[b, tok]):.3e}) vs "
+                                     f"inverse-CDF pick {want} (p={float(probs[b, want]):.3e}), boundary distance {near:.2e}")
+        ids = all_ids[:, step:step + 1]
+    print(f"sampled generate: {n_same}/{B * total} tokens identical to the oracle's inverse-CDF pick at the same uniform, "
+          f"{n_close} on a boundary, {n_in_support}/{B * total} inside the reference's filtered support")
+    assert n_in_support >= B * total - n_close and n_same >= 0.95 * B * total
+    # different seed -> different draw; temperature bound is the reference's assert
+    g2, s2 = m.generate("se", None, None, mix.cuda(), mix.cuda(), seed=seed + 1)
+    assert not (torch.equal(g2.cpu(), gg) and torch.equal(s2.cpu(), ss))
+    with pytest.raises(AssertionError):
+        m.generate("se", None, None, mix.cuda(), mix.cuda(), temperature=1.5)
+
+
+def test_lm_rope_table_grows_and_nan_safe(lib):
+    """positions beyond max_position_embeddings (the reference's rotary embedding has no table limit), a cache
+    that outgrows its capacity, a cache built for another batch, and an all-NaN logit row."""
+    from oracle import llama
+    cfg = llama.lm_small(hidden=128, layers=2, heads=2, gsize=64, ssize=128, feats=64)
+    cfg["llm_base_config"]["max_position_embeddings"] = 96
+    m, sd = build(cfg, 3, 2.0)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 140, 128, generator=g)
+    ref, _ = llama.llm_forward(sd, cfg, x)
+    out = m.llm_forward(x[:, :100].cuda(), use_cache=True, max_new_tokens=8)     # 100 > max_pos 96: table must grow
+    cache = out.past_key_values
+    hs = [out.last_hidden_state]
+    for i in range(100, 140):                                                    # 40 > 8: the cache must grow
+        hs.append(m.llm_forward(x[:, i:i + 1].cuda(), past_key_values=cache, use_cache=True).last_hidden_state)
+    torch.cuda.synchronize()
+    e = rel(torch.cat(hs, 1), ref)
+    print(f"positions past max_position_embeddings + cache growth: rel {e:.2e}, cache capacity {cache.Lmax}")
+    assert e < TOL and cache.length == 140
+    with pytest.raises(ValueError):
+        m.llm_forward(x[:1, :4].cuda(), past_key_values=cache, use_cache=True)   # batch mismatch
+    mix = torch.full((2, 6, 64), float("nan"))
+    gg, ss = m.generate("se", None, None, mix.cuda(), mix.cuda(), do_sample=False)
+    torch.cuda.synchronize()                                                     # no illegal address; ids inside the range
+    assert int(gg.min()) >= 0 and int(gg.max()) < 64 and int(ss.min()) >= 0 and int(ss.max()) < 128

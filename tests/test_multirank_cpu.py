@@ -17,8 +17,13 @@ def _worker(rank, world, port, n_total, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lo, hi = shard_range(n_total, rank, world)
     full = torch.arange(n_total * 3 * 4, dtype=torch.int64).reshape(n_total, 3, 4)   # "tokens" of every clip
-    got = gather_tokens(full[lo:hi].clone(), n_total)
-    ret[rank] = bool(torch.equal(got, full))
+    buffers = {}
+    got = gather_tokens(full[lo:hi].clone(), n_total, buffers=buffers)
+    ok = bool(torch.equal(got, full))
+    if n_total % world == 0:        # equal shards: the preallocated buffer is reused call after call
+        again = gather_tokens(full[lo:hi].clone() + 1, n_total, buffers=buffers)
+        ok = ok and again.data_ptr() == got.data_ptr() and bool(torch.equal(again, full + 1)) and len(buffers) == 1
+    ret[rank] = ok
     dist.destroy_process_group()
 
 
@@ -33,7 +38,8 @@ def test_shard_range_partitions_exactly():
 
 
 def test_token_gather_world2_gloo():
-    world, n_total = 2, 5   # ragged: 3 + 2 clips
-    ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), n_total, ret), nprocs=world, join=True)
-    assert all(ret[r] for r in range(world))
+    for n_total in (5, 8):   # ragged (3 + 2 clips: padded gather) and equal shards (one all_gather_into_tensor into a static buffer)
+        world = 2
+        ret = mp.Manager().dict()
+        mp.spawn(_worker, args=(world, _free_port(), n_total, ret), nprocs=world, join=True)
+        assert all(ret[r] for r in range(world)), n_total

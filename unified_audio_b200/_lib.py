@@ -37,6 +37,7 @@ SIGNATURES = {
     "qb_launch_count_reset": (None, []),
     "qb_gemm": (C.c_int, [C.POINTER(GemmDesc), _vp]),
     "qb_gemm_simt": (C.c_int, [C.POINTER(GemmDesc), _vp]),
+    "qb_gemm_kernel_name": (C.c_char_p, [_i64, _i64, _i32]),
     "qb_split_f16": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "qb_rows_to_planes": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _i64, _i64, _i64, _vp]),
     "qb_bct_to_planes": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp]),
@@ -77,6 +78,8 @@ SIGNATURES = {
     "qb_lm_decode_layer_tc": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp]),
     "qb_lm_head_argmax_tc": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "qb_lm_head_sample_tc": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _i32,
+                                       _f32, _vp, _vp, _vp]),
 }
 
 _lib = None

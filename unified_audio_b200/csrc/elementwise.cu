@@ -522,11 +522,7 @@ static int dwconv7_ln_launch(const float* x, const float* dw_w, const float* dw_
   const int warps = 8;
   const size_t smem = (size_t)warps * C * sizeof(float);
   QB_REQUIRE(smem <= 200 * 1024, "dwconv7_ln: C too large");
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    QB_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  QB_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long total = B * T;
   dwconv7_ln_kernel<<<(unsigned)ceil_div(total, warps), warps * 32, smem, (cudaStream_t)stream>>>(
       x, dw_w, dw_b, ln_w, ln_b, (int)T, (int)C, total, (__half*)hi, (__half*)lo, (long long)ln_bstride);

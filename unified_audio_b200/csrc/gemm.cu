@@ -32,6 +32,13 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+constexpr int QB_MAX_DEVICES = 64;
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < QB_MAX_DEVICES ? dev : 0;
+}
+
 struct RowMapD {
   void* ptr;
   long long ld, rpb, off;
@@ -626,10 +633,11 @@ static int launch_tc(const qb_gemm_desc* d, cudaStream_t st, int num_sms) {
   constexpr int NPL = NTERMS == 1 ? 1 : 2;
   constexpr size_t smem = (size_t)STAGES * NPL * (128 * 64 * 2 + BN * 64 * 2) + 1024 + 256;
   auto kern = gemm_tc_kernel<BN, NTERMS, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[QB_MAX_DEVICES] = {};          // the opt-in shared-memory limit is per-device state
+  const int dev = current_device();
+  if (!attr_set[dev]) {
     QB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   kern<<<grid, GEMM_THREADS, smem, st>>>(mA_hi, mA_lo, mW_hi, mW_lo, p);
@@ -663,10 +671,11 @@ static int launch_tc2(const qb_gemm_desc* d, cudaStream_t st, int num_sms) {
   constexpr int NPL = NTERMS == 1 ? 1 : 2;
   constexpr size_t smem = (size_t)STAGES * NPL * (128 * 64 * 2 + (BN / 2) * 64 * 2) + 1024 + 256;
   auto kern = gemm_tc2_kernel<BN, NTERMS, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[QB_MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (!attr_set[dev]) {
     QB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   int clusters = p.num_tiles < num_sms / 2 ? p.num_tiles : num_sms / 2;
   kern<<<2 * clusters, GEMM_THREADS, smem, st>>>(mA_hi, mA_lo, mW_hi, mW_lo, p);
@@ -676,14 +685,13 @@ static int launch_tc2(const qb_gemm_desc* d, cudaStream_t st, int num_sms) {
 }
 
 static int num_sms_cached() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (const char* e = getenv("QB_GEMM_SMS")) n = atoi(e);
+  static int n[QB_MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (!n[dev]) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (const char* e = getenv("QB_GEMM_SMS")) n[dev] = atoi(e);
   }
-  return n;
+  return n[dev];
 }
 
 }  // namespace qb
@@ -695,26 +703,49 @@ extern "C" int qb_version(void) { return 100; }
 extern "C" int64_t qb_launch_count(void) { return (int64_t)g_launches.load(); }
 extern "C" void qb_launch_count_reset(void) { g_launches = 0; }
 
-extern "C" int qb_gemm(const qb_gemm_desc* d, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  QB_REQUIRE(d != nullptr, "gemm: null desc");
-  const bool split = d->a_lo != nullptr;
-  int bn = d->n > 128 ? 256 : 128;
+// kernel variant for a problem shape (one place: qb_gemm dispatches on it, qb_gemm_kernel_name reports it)
+enum GemmVariant { GV_PAIR_SINGLE, GV_PAIR_SPLIT, GV_TC_256_SINGLE, GV_TC_128_SINGLE, GV_TC_256_SPLIT, GV_TC_128_SPLIT };
+static GemmVariant pick_variant(int64_t m_per_batch, int64_t n, bool split) {
+  int bn = n > 128 ? 256 : 128;
   if (split) bn = 128;
   static const char* env_bn = getenv("QB_GEMM_BN_SPLIT");
   if (split && env_bn) bn = atoi(env_bn);
-  if (d->n <= 128) bn = 128;
-  const int sms = num_sms_cached();
+  if (n <= 128) bn = 128;
   // CTA pairs (256-row tiles) when they do not add row padding and the N extent fills a 256-wide tile
   static const int pair_mode = getenv("QB_GEMM_PAIR") ? atoi(getenv("QB_GEMM_PAIR")) : 1;
   // (a pair tile that is 3/4 full in N still halves the operand bytes each SM ingests per MMA; up to 3 % of padded rows
   //  per batch are accepted - the 1-CTA kernel is ingest-bound on every conv shape of the BiCodec generator)
-  const long long m256 = ceil_div(d->m_per_batch, 256) * 256;
-  const bool pair_ok = pair_mode && d->n >= 192 &&
-                       (ceil_div(d->m_per_batch, 256) * 2 == ceil_div(d->m_per_batch, 128) || m256 * 100 <= d->m_per_batch * 103);
-  if (pair_ok) return split ? launch_tc2<256, 3, 3>(d, st, sms) : launch_tc2<256, 1, 6>(d, st, sms);
-  if (!split) return bn == 256 ? launch_tc<256, 1, 4>(d, st, sms) : launch_tc<128, 1, 6>(d, st, sms);
-  return bn == 256 ? launch_tc<256, 3, 2>(d, st, sms) : launch_tc<128, 3, 3>(d, st, sms);
+  const long long m256 = ceil_div(m_per_batch, 256) * 256;
+  const bool pair_ok = pair_mode && n >= 192 &&
+                       (ceil_div(m_per_batch, 256) * 2 == ceil_div(m_per_batch, 128) || m256 * 100 <= m_per_batch * 103);
+  if (pair_ok) return split ? GV_PAIR_SPLIT : GV_PAIR_SINGLE;
+  if (!split) return bn == 256 ? GV_TC_256_SINGLE : GV_TC_128_SINGLE;
+  return bn == 256 ? GV_TC_256_SPLIT : GV_TC_128_SPLIT;
+}
+
+extern "C" const char* qb_gemm_kernel_name(int64_t m_per_batch, int64_t n, int32_t split) {
+  switch (pick_variant(m_per_batch, n, split != 0)) {
+    case GV_PAIR_SINGLE: return "gemm_tc2_kernel<256,1,6> (cta_group::2)";
+    case GV_PAIR_SPLIT: return "gemm_tc2_kernel<256,3,3> (cta_group::2)";
+    case GV_TC_256_SINGLE: return "gemm_tc_kernel<256,1,4>";
+    case GV_TC_128_SINGLE: return "gemm_tc_kernel<128,1,6>";
+    case GV_TC_256_SPLIT: return "gemm_tc_kernel<256,3,2>";
+    default: return "gemm_tc_kernel<128,3,3>";
+  }
+}
+
+extern "C" int qb_gemm(const qb_gemm_desc* d, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  QB_REQUIRE(d != nullptr, "gemm: null desc");
+  const int sms = num_sms_cached();
+  switch (pick_variant(d->m_per_batch, d->n, d->a_lo != nullptr)) {
+    case GV_PAIR_SINGLE: return launch_tc2<256, 1, 6>(d, st, sms);
+    case GV_PAIR_SPLIT: return launch_tc2<256, 3, 3>(d, st, sms);
+    case GV_TC_256_SINGLE: return launch_tc<256, 1, 4>(d, st, sms);
+    case GV_TC_128_SINGLE: return launch_tc<128, 1, 6>(d, st, sms);
+    case GV_TC_256_SPLIT: return launch_tc<256, 3, 2>(d, st, sms);
+    default: return launch_tc<128, 3, 3>(d, st, sms);
+  }
 }
 
 extern "C" int qb_gemm_simt(const qb_gemm_desc* d, void* stream) {

@@ -496,10 +496,11 @@ lm_decode_attn_kernel(const float* __restrict__ q, const float* __restrict__ kc,
 __global__ void lm_argmax_embed_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int n_part,
                                        int B, const float* __restrict__ emb, int Hd, float* __restrict__ x_next,
                                        int64_t* __restrict__ out_ids, int out_stride, int* __restrict__ pos,
-                                       int* __restrict__ slot) {
+                                       int* __restrict__ slot, const int* __restrict__ range, int vocab) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");          // no-ops unless launched as a programmatic dependent
   const int b = blockIdx.x;
+  const int range_lo = range[0];
   __shared__ float sv[32];
   __shared__ int si[32];
   float bv = -INFINITY;
@@ -520,6 +521,9 @@ __global__ void lm_argmax_embed_kernel(const float* __restrict__ part_val, const
   if (threadIdx.x == 0) {
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
       if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
+    // an all-NaN logit row never wins a comparison (bi stays at its sentinel): fall back to the first column of the
+    // range like torch.argmax returning a valid index, instead of gathering emb[0x7fffffff]
+    if ((unsigned)bi >= (unsigned)vocab) bi = range_lo;
     si[0] = bi;
     out_ids[(size_t)b * out_stride + *slot] = (int64_t)bi;
   }
@@ -535,6 +539,146 @@ __global__ void lm_argmax_embed_kernel(const float* __restrict__ part_val, const
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ sampled decoding
+// CustomLlamaModel.sample_logits (QuarkAudio-UniSE/model/llm/llm.py:253-289) for one row per CTA, on the range-restricted
+// logits the head kernel wrote: top-k (threshold = k-th largest value, ties kept: `logits < topk[-1]` is what is removed)
+// -> top-p over softmax of the SURVIVORS sorted descending (a token is removed when the cumulative probability of the
+// tokens BEFORE it already exceeds top_p; the first one always stays) -> / temperature -> softmax -> one multinomial
+// draw.  torch.multinomial's generator cannot be reproduced bit for bit, so the draw is defined here as the inverse CDF
+// over the kept tokens in descending-logit order (ties: ascending id) at u = Philox4x32-10(key = seed, counter =
+// {step, row, call, 0}).x * 2^-32 truncated to 24 bits: same distribution, replayable from (seed, call, step, row).
+constexpr int LS_MAX = 1024;             // survivors kept (top_k + ties); top_k <= LS_MAX enforced by the host
+__device__ __forceinline__ uint32_t ls_key(float v) {     // monotone float -> uint32 (NaN sorts lowest)
+  if (v != v) return 0u;
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ls_val(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ uint32_t philox_u32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+
+__global__ void __launch_bounds__(256)
+lm_sample_embed_kernel(const float* __restrict__ logits, int ld, const int* __restrict__ range, int B, float inv_temp,
+                       int top_k, float top_p, const unsigned* __restrict__ seed /* {seed_lo, seed_hi, call, 0} */,
+                       const float* __restrict__ emb, int Hd, float* __restrict__ x_next, int64_t* __restrict__ out_ids,
+                       int out_stride, int* __restrict__ pos, int* __restrict__ slot, float* __restrict__ dbg) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  extern __shared__ uint32_t ls_smem[];
+  const int lo = range[0], n = range[1] - lo, b = blockIdx.x, tid = threadIdx.x;
+  uint32_t* keys = ls_smem;                       // [n]
+  uint32_t* skey = keys + ((n + 3) & ~3);         // [LS_MAX] survivors: key
+  int* sidx = (int*)(skey + LS_MAX);              // [LS_MAX] survivors: column
+  __shared__ int hist[256];
+  __shared__ uint32_t sh_prefix;
+  __shared__ int sh_need, sh_cnt, sh_tok;
+  for (int i = tid; i < n; i += 256) keys[i] = ls_key(logits[(size_t)b * ld + i]);
+  if (tid == 0) { sh_prefix = 0u; sh_need = top_k < n ? top_k : n; sh_cnt = 0; }
+  __syncthreads();
+  // ---- radix select of the top_k-th largest key, one byte per pass from the top
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    hist[tid] = 0;
+    __syncthreads();
+    const uint32_t prefix = sh_prefix, himask = shift == 24 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int i = tid; i < n; i += 256) {
+      const uint32_t k = keys[i];
+      if ((k & himask) == prefix) atomicAdd(&hist[(k >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int need = sh_need, bin = 255;
+      for (; bin > 0; --bin) {
+        if (hist[bin] >= need) break;
+        need -= hist[bin];
+      }
+      sh_need = need;
+      sh_prefix = prefix | ((uint32_t)bin << shift);
+    }
+    __syncthreads();
+  }
+  const uint32_t thr = sh_prefix;
+  // ---- survivors (key >= threshold: ties at the k-th value stay, llm.py:263-264), then bitonic sort descending
+  for (int i = tid; i < n; i += 256) {
+    const uint32_t k = keys[i];
+    if (k >= thr) {
+      const int s = atomicAdd(&sh_cnt, 1);
+      if (s < LS_MAX) { skey[s] = k; sidx[s] = i; }
+    }
+  }
+  __syncthreads();
+  const int cnt = sh_cnt < LS_MAX ? sh_cnt : LS_MAX;
+  int P = 1;
+  while (P < cnt) P <<= 1;
+  for (int i = cnt + tid; i < P; i += 256) { skey[i] = 0u; sidx[i] = 0x7fffffff; }
+  __syncthreads();
+  for (int k2 = 2; k2 <= P; k2 <<= 1)
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P; i += 256) {
+        const int l = i ^ j;
+        if (l > i) {
+          const uint32_t ka = skey[i], kb = skey[l];
+          const int ia = sidx[i], ib = sidx[l];
+          const bool a_first = ka > kb || (ka == kb && ia < ib);       // descending by key, ascending by column on ties
+          const bool up = (i & k2) == 0;
+          if (up != a_first) { skey[i] = kb; skey[l] = ka; sidx[i] = ib; sidx[l] = ia; }
+        }
+      }
+      __syncthreads();
+    }
+  // ---- top-p cut, temperature, inverse-CDF draw (one thread: <= LS_MAX sequential fp32 adds, like torch.cumsum on a row)
+  if (tid == 0) {
+    const float m = ls_val(skey[0]);
+    int nk = cnt;
+    if (top_p < 1.0f) {
+      float Z = 0.f;
+      for (int i = 0; i < cnt; ++i) Z += expf(ls_val(skey[i]) - m);
+      float cum = 0.f;
+      nk = 1;
+      for (int i = 1; i < cnt; ++i) {
+        cum += expf(ls_val(skey[i - 1]) - m) / Z;
+        if (cum > top_p) break;
+        nk = i + 1;
+      }
+    }
+    float S = 0.f;
+    for (int i = 0; i < nk; ++i) S += expf((ls_val(skey[i]) - m) * inv_temp);
+    const uint32_t r = philox_u32(seed[0], seed[1], (uint32_t)*slot, (uint32_t)b, seed[2], 0u);
+    const float u = (float)(r >> 8) * (1.0f / 16777216.0f);
+    const float target = u * S;
+    float run = 0.f;
+    int pick = nk - 1;
+    for (int i = 0; i < nk; ++i) {
+      run += expf((ls_val(skey[i]) - m) * inv_temp);
+      if (run > target) { pick = i; break; }
+    }
+    int tok = lo + sidx[pick];
+    if (sidx[pick] == 0x7fffffff || m != m) tok = lo;          // all-NaN row: first column of the range (see arg-max kernel)
+    sh_tok = tok;
+    out_ids[(size_t)b * out_stride + *slot] = (int64_t)tok;
+    if (dbg) { dbg[b * 4 + 0] = u; dbg[b * 4 + 1] = (float)cnt; dbg[b * 4 + 2] = (float)nk; dbg[b * 4 + 3] = S; }
+  }
+  __syncthreads();
+  const int tok = sh_tok;
+  for (int k = tid; k < Hd; k += 256) x_next[(size_t)b * Hd + k] = emb[(size_t)tok * Hd + k];
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const int done = atomicAdd(slot + 1, 1);
+    if (done == B - 1) { slot[1] = 0; *slot += 1; *pos += 1; }
+  }
+}
 
 // ------------------------------------------------------------------------------------------ decode step, tensor-core path
 // The fp32 SIMT kernels above spend their time in shared-memory reads (every warp re-reads the whole x tile for
@@ -568,6 +712,8 @@ struct SkParams {
   float* part_val;
   int* part_idx;
   int pdl_early;         // 1: release the dependent grid before the dependency wait (deep pile-up), 0: after the K loop
+  float* logits;         // HEAD: optional full logits of the range [B][logits_ld] (sampled decoding); NULL = arg-max partials only
+  int logits_ld;
 };
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -715,6 +861,11 @@ lm_skinny_kernel(const SkParams p) {
     if (cta_active && b < p.B) {
       bv = v0; bi = row0 + c;
       if (v1 > bv) { bv = v1; bi = row0 + 8 + c; }
+      if (p.logits) {
+        float* lg = p.logits + (size_t)b * p.logits_ld + (row0 - p.range[0]);
+        lg[c] = v0;
+        lg[8 + c] = v1;
+      }
     }
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
@@ -847,11 +998,7 @@ extern "C" int qb_lm_flash_attn(const float* q32, const float* k_cache, const fl
   QB_REQUIRE(q32 && k_cache && v_cache && out_hi && L > 0, "lm_flash_attn: bad args");
   dim3 grid((unsigned)ceil_div(L, LF_BQ), (unsigned)heads, (unsigned)B);
   const size_t smem = (size_t)(2 * LF_BQ + 4 * LF_BK) * LF_P * sizeof(__half);
-  static bool set = false;
-  if (!set) {
-    QB_CHECK_CUDA(cudaFuncSetAttribute(lm_flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    set = true;
-  }
+    QB_CHECK_CUDA(cudaFuncSetAttribute(lm_flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per-device state: set on every launch (cheap)
   lm_flash_attn_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(q32, k_cache, v_cache, (int)L, heads, pos0, Lmax,
                                                                  (__half*)out_hi, (__half*)out_lo);
   g_launches++;
@@ -861,12 +1008,8 @@ extern "C" int qb_lm_flash_attn(const float* q32, const float* k_cache, const fl
 
 template <int MODE, bool MULTI>
 static int launch_gemv_t(const LmGemvParams& p, int n_items_max, cudaStream_t st) {
-  static bool set = false;
-  const size_t smem = (size_t)32 * LM_KT * sizeof(float);
-  if (!set) {
-    QB_CHECK_CUDA(cudaFuncSetAttribute(lm_gemv_kernel<MODE, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    set = true;
-  }
+    const size_t smem = (size_t)32 * LM_KT * sizeof(float);
+  QB_CHECK_CUDA(cudaFuncSetAttribute(lm_gemv_kernel<MODE, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per-device state: set on every launch (cheap)
   lm_gemv_kernel<MODE, MULTI><<<(unsigned)ceil_div(n_items_max, LM_WARPS), LM_WARPS * 32, smem, st>>>(p);
   g_launches++;
   QB_CHECK_CUDA(cudaGetLastError());
@@ -891,12 +1034,8 @@ extern "C" int qb_lm_decode_layer(float* x, int64_t B, int32_t hidden, int32_t h
   // RMSNorm + QKV + RoPE + cache append
   p.x = x; p.K = hidden; p.W = wqkv; p.norm_w = in_norm; p.out = q_buf; p.n_items = 3 * heads * 32;
   if (int e = launch_gemv<LM_QKV>(p, p.n_items, st)) return e;
-  static bool attn_set = false;
-  const size_t asmem = (size_t)Lmax * sizeof(float);
-  if (!attn_set) {
-    QB_CHECK_CUDA(cudaFuncSetAttribute(lm_decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attn_set = true;
-  }
+    const size_t asmem = (size_t)Lmax * sizeof(float);
+  QB_CHECK_CUDA(cudaFuncSetAttribute(lm_decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));   // per-device state: set on every launch (cheap)
   QB_REQUIRE(asmem <= 64 * 1024, "lm_decode_layer: Lmax too large for the score buffer");
   lm_decode_attn_kernel<<<dim3((unsigned)heads, (unsigned)B), 128, asmem, st>>>(q_buf, k_cache, v_cache, heads, Lmax, pos,
                                                                               attn_buf);
@@ -926,7 +1065,7 @@ extern "C" int qb_lm_head_argmax(const float* x, int64_t B, int32_t hidden, cons
   if (int e = launch_gemv<LM_HEAD>(p, max_cols / 2, st)) return e;
   const int n_part = (int)ceil_div(max_cols / 2, LM_WARPS);
   lm_argmax_embed_kernel<<<(unsigned)B, 128, 0, st>>>(part_val, part_idx, n_part, (int)B, embedding, hidden, x_next,
-                                                     out_ids, out_stride, pos, slot);
+                                                     out_ids, out_stride, pos, slot, range, 0x7ffffffe);
   g_launches++;
   QB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1023,6 +1162,31 @@ extern "C" int qb_lm_head_argmax_tc(const float* x, int64_t B, int32_t hidden, c
   if (int e = launch_skinny<SK_HEAD>(p, max_cols / 16, st)) return e;
   QB_CHECK_CUDA(launch_pdl(lm_argmax_embed_kernel, dim3((unsigned)B), dim3(128), 0, st, (const float*)part_val,
                            (const int*)part_idx, (int)(max_cols / 16), (int)B, embedding, (int)hidden, x_next, out_ids,
-                           (int)out_stride, (int*)pos, (int*)slot));
+                           (int)out_stride, (int*)pos, (int*)slot, (const int*)range, 0x7ffffffe));
+  return 0;
+}
+
+// Sampled decoding step: as qb_lm_head_argmax_tc, but the head writes the full range logits [B][max_cols] and the token is
+// drawn by lm_sample_embed_kernel (top-k -> top-p -> temperature -> multinomial, llm.py:253-289).
+extern "C" int qb_lm_head_sample_tc(const float* x, int64_t B, int32_t hidden, const qb_half* w_head, const int32_t* range,
+                                    int32_t max_cols, const float* embedding, float* x_next, int64_t* out_ids,
+                                    int32_t out_stride, int32_t* pos, int32_t* slot, float* part_val, int32_t* part_idx,
+                                    float* logits, float temperature, int32_t top_k, float top_p, const uint32_t* seed,
+                                    float* debug, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  QB_REQUIRE(B >= 1 && B <= 32 && max_cols % 16 == 0, "lm_head_sample_tc: bad args (max_cols must be a multiple of 16)");
+  QB_REQUIRE(logits && seed, "lm_head_sample_tc: logits / seed buffers required");
+  QB_REQUIRE(temperature > 0.f && temperature <= 1.0f, "lm_head_sample_tc: temperature must be in (0, 1] (llm.py:278)");
+  QB_REQUIRE(top_k >= 1 && top_k <= LS_MAX, "lm_head_sample_tc: top_k must be in 1..%d (got %d)", LS_MAX, top_k);
+  SkParams p = {};
+  p.B = (int)B; p.eps = 1e-6f; p.x = x; p.K = hidden; p.W = (const uint4*)w_head; p.range = range;
+  p.part_val = part_val; p.part_idx = part_idx; p.pdl_early = lm_pdl_early(); p.logits = logits; p.logits_ld = max_cols;
+  if (int e = launch_skinny<SK_HEAD>(p, max_cols / 16, st)) return e;
+  const size_t smem = ((size_t)((max_cols + 3) & ~3) + 2 * LS_MAX) * 4;
+    QB_CHECK_CUDA(cudaFuncSetAttribute(lm_sample_embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));   // per-device state: set on every launch (cheap)
+  QB_REQUIRE(smem <= 160 * 1024, "lm_head_sample_tc: range too wide (%d columns)", max_cols);
+  QB_CHECK_CUDA(launch_pdl(lm_sample_embed_kernel, dim3((unsigned)B), dim3(256), smem, st, (const float*)logits, (int)max_cols,
+                           (const int*)range, (int)B, 1.0f / temperature, (int)top_k, top_p, (const unsigned*)seed, embedding,
+                           (int)hidden, x_next, out_ids, (int)out_stride, (int*)pos, (int*)slot, debug));
   return 0;
 }

@@ -56,11 +56,24 @@ class StaticKVCache:
     def __init__(self, layers, B, heads, Lmax, device):
         self.k = [torch.zeros(B, heads, Lmax, 64, dtype=torch.float32, device=device) for _ in range(layers)]
         self.v = [torch.zeros(B, heads, Lmax, 64, dtype=torch.float32, device=device) for _ in range(layers)]
-        self.B, self.Lmax, self.length = B, Lmax, 0
+        self.B, self.heads, self.layers, self.Lmax, self.length = B, heads, layers, Lmax, 0
         self.pos = torch.zeros(1, dtype=torch.int32, device=device)     # device copy used by the decode kernels
 
     def get_seq_length(self):
         return self.length
+
+    def reserve(self, n_positions: int):
+        """Make room for `n_positions` in total (HF DynamicCache grows without bound, llm.py:189-193): reallocate to the
+        next multiple of 256 and copy the filled prefix.  Captured graphs never call this (their capacity is fixed)."""
+        if n_positions <= self.Lmax:
+            return
+        new = -(-n_positions // 256) * 256
+        for buf in (self.k, self.v):
+            for i, t in enumerate(buf):
+                g = torch.zeros(self.B, self.heads, new, 64, dtype=t.dtype, device=t.device)
+                g[:, :, :self.length] = t[:, :, :self.length]
+                buf[i] = g
+        self.Lmax = new
 
 
 @dataclass
@@ -134,15 +147,28 @@ class LLM_SFT(nn.Module):
             L = layers[-1]       # product decode path: the same folded weights packed as fp16 {hi[4], lo[4]} groups
             L.update(wqkv_p=ops.lm_pack_weight(L["wqkv32"]), wo_p=ops.lm_pack_weight(L["wo32"]), wg_p=ops.lm_pack_weight(L["wg32"]),
                      wu_p=ops.lm_pack_weight(L["wu32"]), wd_p=ops.lm_pack_weight(L["wd32"]))
-        inv = 1.0 / (10000.0 ** (torch.arange(0, 64, 2, dtype=torch.int64).float() / 64))
-        fr = torch.arange(self.max_pos).float()[:, None] * inv[None, :]
-        emb = torch.cat((fr, fr), -1)
         self._w = dict(layers=layers, norm=sd["norm.weight"].contiguous(), head=Planes.from_f32(sd["output_head.weight"], True),
                        head32=(sd["output_head.weight"] * sd["norm.weight"][None, :]).contiguous(), emb=sd["codec_embedding.weight"].contiguous(),
                        adapter=Planes.from_f32(sd["adapter.weight"], True), adapter_b=sd["adapter.bias"].contiguous(),
-                       cos=emb.cos().to(dev).contiguous(), sin=emb.sin().to(dev).contiguous())
+                       cos=None, sin=None, rope_rows=0)
         self._w["head_p"] = ops.lm_pack_weight(self._w["head32"])
+        self._ensure_rope(self.max_pos)
         return self._w
+
+    def _ensure_rope(self, n_positions: int):
+        """cos/sin tables cover positions [0, rope_rows).  The reference's HF rotary embedding computes them from position_ids
+        on the fly and has no length limit (llm.py:187), so the table grows on demand (the kernels index it unguarded:
+        every caller checks pos0 + L against it first).  Growing replaces the tensors, so captured decode graphs that hold
+        the old pointers are dropped."""
+        W = self._w
+        if W["rope_rows"] >= n_positions:
+            return
+        rows = max(self.max_pos, -(-n_positions // 1024) * 1024)
+        inv = 1.0 / (10000.0 ** (torch.arange(0, 64, 2, dtype=torch.int64).float() / 64))
+        fr = torch.arange(rows).float()[:, None] * inv[None, :]
+        emb = torch.cat((fr, fr), -1)
+        W["cos"], W["sin"], W["rope_rows"] = emb.cos().to(self._dev()).contiguous(), emb.sin().to(self._dev()).contiguous(), rows
+        self._gen_state = {}
 
     def _buf(self, name, shape, dtype=torch.float32):
         key = (name, tuple(shape), dtype)
@@ -168,6 +194,11 @@ class LLM_SFT(nn.Module):
         pos0 = cache.length
         if pos0 + L > cache.Lmax:
             raise ValueError("KV cache too small")
+        if cache.B != B or cache.heads != heads or cache.layers != self.n_layers:
+            raise ValueError(f"KV cache built for batch {cache.B} x {cache.heads} heads x {cache.layers} layers, "
+                             f"got batch {B} x {heads} heads x {self.n_layers} layers")
+        self._ensure_rope(pos0 + L)
+        W = self._w
         t1 = self._planes("t1", (M, H))
         hid = self._planes("hid", (M, inter))
         qkv = self._buf("qkv", (M, 3 * H))
@@ -196,19 +227,25 @@ class LLM_SFT(nn.Module):
 
     @torch.no_grad()
     def llm_forward(self, inputs_embeds, attention_mask=None, past_key_values: Optional[StaticKVCache] = None,
-                    use_cache: bool = False, **unused) -> LMOutput:
-        """llm.py:150-228 (mask None + SDPA == causal)."""
+                    use_cache: bool = False, max_new_tokens: Optional[int] = None, **unused) -> LMOutput:
+        """llm.py:150-228 (mask None + SDPA == causal).  `max_new_tokens` (optional) sizes a newly created cache; a cache
+        that fills up is grown (reallocate + copy) like the reference's DynamicCache."""
         if attention_mask is not None:
             raise NotImplementedError("only the reference's causal (mask=None) path is implemented")
         W = self._prepare()
         B, L, H = inputs_embeds.shape
         cache = past_key_values
         if cache is None:
-            cache = StaticKVCache(self.n_layers, B, self.heads, max(64, -(-L // 64) * 64 + (1024 if use_cache else 0)), self._dev())
+            extra = (max_new_tokens if max_new_tokens is not None else 1024) if use_cache else 0
+            cache = StaticKVCache(self.n_layers, B, self.heads, max(64, -(-(L + extra) // 64) * 64), self._dev())
+        if cache.B != B or cache.heads != self.heads or cache.layers != self.n_layers:
+            raise ValueError(f"KV cache built for batch {cache.B} x {cache.heads} heads x {cache.layers} layers, "
+                             f"got batch {B} x {self.heads} heads x {self.n_layers} layers")
+        cache.reserve(cache.length + L)
+        self._ensure_rope(cache.length + L)
+        W = self._w
         x = inputs_embeds.float().reshape(B * L, H).contiguous().clone()
         if L == 1 and B <= 32 and cache.length > 0:
-            if cache.length + 1 > cache.Lmax:
-                raise ValueError("KV cache too small")
             self._decode_layers(x, B, cache)
             cache.length += 1
             cache.pos.fill_(cache.length)
@@ -280,32 +317,49 @@ class LLM_SFT(nn.Module):
     @torch.no_grad()
     def generate(self, task_name, enroll_mel, enroll_feats, mix_mel, mix_feats, global_length: int = 32,
                  temperature: float = 0.8, top_k: int = 50, top_p: float = 0.95, do_sample: bool = True,
-                 use_cuda_graph: bool = True):
+                 use_cuda_graph: bool = True, seed: Optional[int] = None):
+        """llm_sft.py:93-195 with the reference's signature and defaults.  do_sample=True draws every token on the device
+        (top-k -> top-p -> temperature -> multinomial, csrc/llm.cu lm_sample_embed_kernel); `seed` (default: torch's
+        global generator) makes the draw reproducible.  Greedy decoding ignores temperature / top_k / top_p exactly as the
+        reference's arg-max does (filters never remove the arg-max, llm.py:263-287)."""
+        sampling = None
         if do_sample:
-            raise NotImplementedError("only greedy decoding (do_sample=False, the shipped test setting model.py:173) "
-                                      "is implemented natively; top-k/top-p never remove the arg-max (llm.py:263-287)")
+            if self.decode_kernel != "tc":
+                raise NotImplementedError("sampled decoding runs on the tensor-core decode path only (QB_LM_DECODE=tc)")
+            if not (0.0 < temperature <= 1.0):
+                raise AssertionError("0 < temperature <= 1.0 (llm.py:278)")
+            if top_k <= 0 or top_k > 1024:
+                raise NotImplementedError("native sampling supports 1 <= top_k <= 1024 (reference default 50)")
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            sampling = dict(temperature=float(temperature), top_k=int(top_k), top_p=float(top_p), seed=int(seed))
         semantic_length = mix_mel.size(1)
         Ball = mix_feats.shape[0]
         outs_g, outs_s = [], []
-        for b0 in range(0, Ball, 32):      # decode kernels keep <= 32 sequences' rows in registers
+        for ci, b0 in enumerate(range(0, Ball, 32)):      # decode kernels keep <= 32 sequences' rows in registers
             sl = slice(b0, min(b0 + 32, Ball))
+            if sampling is not None:
+                sampling["call"] = ci
             gi, si = self._generate_chunk(task_name, None if enroll_mel is None else enroll_feats[sl], mix_feats[sl],
-                                          semantic_length, global_length, use_cuda_graph)
+                                          semantic_length, global_length, use_cuda_graph, sampling)
             outs_g.append(gi)
             outs_s.append(si)
         return torch.cat(outs_g, 0), torch.cat(outs_s, 0)
 
-    def _generate_chunk(self, task_name, enroll_feats, mix_feats, semantic_length, global_length, use_graph):
+    def _generate_chunk(self, task_name, enroll_feats, mix_feats, semantic_length, global_length, use_graph, sampling=None):
         W = self._prepare()
         dev = mix_feats.device
         prefix = self._prefix(task_name, enroll_feats, mix_feats)
         B, P, H = prefix.shape
         n_steps = global_length + 1 + semantic_length
         Lmax = -(-(P + n_steps) // 64) * 64
+        self._ensure_rope(P + n_steps)
+        W = self._w
         max_cols = max(self.global_size, self.semantic_size)
+        samp_key = None if sampling is None else (sampling["temperature"], sampling["top_k"], sampling["top_p"])
         # Decode state (KV cache, counters, output ids) and the captured graphs are kept per shape: capturing and
         # instantiating ~560 kernel nodes costs the host 10-50 ms, as much as the whole generation takes on the device.
-        key = (B, P, n_steps, bool(use_graph), self.decode_kernel, int(self.graph_steps), str(dev))
+        key = (B, P, n_steps, bool(use_graph), self.decode_kernel, int(self.graph_steps), str(dev), samp_key)
         st = self._gen_state.get(key)
         if st is None:
             self._gen_state.clear()                    # one shape at a time (the cache is ~0.9 GB at B=32)
@@ -314,19 +368,30 @@ class LLM_SFT(nn.Module):
                       rng=torch.zeros(2, dtype=torch.int32, device=dev), slot=torch.zeros(2, dtype=torch.int32, device=dev),
                       out_ids=torch.zeros(B, n_steps, dtype=torch.int64, device=dev),
                       pv=torch.zeros(max_cols // 16 + 1, 32, device=dev),
-                      pi=torch.zeros(max_cols // 16 + 1, 32, dtype=torch.int32, device=dev), g1=None, gk=None, captured=False)
+                      pi=torch.zeros(max_cols // 16 + 1, 32, dtype=torch.int32, device=dev), g1=None, gk=None, captured=False,
+                      logits=torch.zeros(B, max_cols, device=dev) if sampling is not None else None,
+                      seed=torch.zeros(4, dtype=torch.int32, device=dev), dbg=torch.zeros(B, 4, device=dev))
             self._gen_state[key] = st
         cache, xs, rng, slot, out_ids, pv, pi = (st[k] for k in ("cache", "xs", "rng", "slot", "out_ids", "pv", "pi"))
         cache.length = 0
         cache.pos.zero_()
         slot.zero_()
+        if sampling is not None:        # Philox key / call counter live in device memory: the captured graph is reused across seeds
+            sd_ = sampling["seed"]
+            to_i32 = lambda v: v - (1 << 32) if v >= (1 << 31) else v
+            st["seed"].copy_(torch.tensor([to_i32(sd_ & 0xFFFFFFFF), to_i32((sd_ >> 32) & 0xFFFFFFFF), sampling["call"], 0],
+                                          dtype=torch.int32), non_blocking=True)
         rng.copy_(torch.tensor([self.global_offset, self.global_offset + self.global_size], dtype=torch.int32), non_blocking=True)
         x = prefix.reshape(B * P, H).contiguous().clone()
         self._prefill(x, B, P, cache)
 
         def step():
             self._decode_layers(xs, B, cache)
-            if self.decode_kernel == "tc":
+            if sampling is not None:
+                ops.lm_head_sample_tc(xs, B, H, W["head_p"], rng, max_cols, W["emb"], xs, out_ids, n_steps, cache.pos, slot, pv, pi,
+                                      st["logits"], sampling["temperature"], sampling["top_k"], sampling["top_p"], st["seed"],
+                                      st["dbg"])
+            elif self.decode_kernel == "tc":
                 ops.lm_head_argmax_tc(xs, B, H, W["head_p"], rng, max_cols, W["emb"], xs, out_ids, n_steps, cache.pos, slot,
                                       pv, pi)
             else:

@@ -77,6 +77,10 @@ def gemm(a: Planes, w: Planes, n: int, *, a_batch: int, a_rows_per_batch: int, a
     _lib.check((lib.qb_gemm_simt if simt else lib.qb_gemm)(C.byref(d), _stream()))
 
 
+def gemm_kernel_name(m_per_batch: int, n: int, split: bool) -> str:
+    return _lib.load().qb_gemm_kernel_name(m_per_batch, n, int(split)).decode()
+
+
 def split_f16(x: torch.Tensor, out: Planes):
     _lib.check(_lib.load().qb_split_f16(_p(x), _p(out.hi), _p(out.lo), x.numel(), _stream()))
 
@@ -279,6 +283,13 @@ def lm_decode_layer_tc(x, B, hidden, heads, inter, L, kc, vc, Lmax, pos, cos, si
 def lm_head_argmax_tc(x, B, hidden, w_head_p, rng, max_cols, emb, x_next, out_ids, out_stride, pos, slot, pv, pi):
     _lib.check(_lib.load().qb_lm_head_argmax_tc(_p(x), B, hidden, _p(w_head_p), _p(rng), max_cols, _p(emb), _p(x_next),
                                                 _p(out_ids), out_stride, _p(pos), _p(slot), _p(pv), _p(pi), _stream()))
+
+
+def lm_head_sample_tc(x, B, hidden, w_head_p, rng, max_cols, emb, x_next, out_ids, out_stride, pos, slot, pv, pi, logits,
+                      temperature, top_k, top_p, seed, debug=None):
+    _lib.check(_lib.load().qb_lm_head_sample_tc(_p(x), B, hidden, _p(w_head_p), _p(rng), max_cols, _p(emb), _p(x_next),
+                                                _p(out_ids), out_stride, _p(pos), _p(slot), _p(pv), _p(pi), _p(logits),
+                                                float(temperature), int(top_k), float(top_p), _p(seed), _p(debug), _stream()))
 
 
 def launch_count() -> int:
