@@ -81,6 +81,7 @@ def random_init_(model, seed: int):
                               for i in range(q.num_quantizers)], 0)
             q.set_codebooks(cb)
     model._w = None
+    model._engine = None
 
 
 class ClockSampler:
@@ -272,13 +273,14 @@ def build_lm(dev):
     return m
 
 
-def lm_decode_bytes(B, P, world):
+def lm_decode_bytes(B, P, world, chunks=None):
     """SURVEY 8(d) algorithmic bytes of one generation: per decode step the fp32-equivalent layer weights (4 B / parameter:
     the packed fp16 hi/lo groups are the same size) + the active head slice + the fp32 KV read / write of every sequence."""
     w_layers = 12 * (4 * 512 * 512 + 3 * 512 * 2048) * 4
     head = 33 * 4096 * 512 * 4 + 250 * 8192 * 512 * 4
     kv = sum(B * 2 * 12 * 512 * 4 * (P + i + 1) for i in range(283))
-    return world * (283 * w_layers + head) + kv        # B is already the whole-job batch; every rank streams its own replica
+    # B is the whole-job batch; the weights are streamed once per generation chunk (<= 32 sequences) on every rank
+    return (chunks if chunks is not None else world) * (283 * w_layers + head) + kv
 
 
 def bench_lm_generate(args, ctx, m, task, B_local, total_batch=None, with_cpu=False, steps=None):
@@ -322,7 +324,14 @@ def bench_lm_generate(args, ctx, m, task, B_local, total_batch=None, with_cpu=Fa
     ms_e2e = ctx.timed(e2e_step, steps)
     P = 503 if task == "tse" else 252
     peaks = load_peaks()
-    gbs = lm_decode_bytes(B_all, P, world) / (ms * 1e-3) / 1e9
+    chunks_local = -(-B_local // 32)
+    if ctx.dist is not None:
+        tch = torch.tensor([chunks_local], device=dev)
+        ctx.dist.all_reduce(tch)
+        chunks_all = int(tch)
+    else:
+        chunks_all = chunks_local
+    gbs = lm_decode_bytes(B_all, P, world, chunks_all) / (ms * 1e-3) / 1e9
     name = "sr" if task == "se" else "tse"
     out = dict(metric=f"unise_{name}_arlm_generate_tokens_per_s", value=B_all * 283 / (ms * 1e-3), unit="tokens/s", n_gpus=world,
                steps=steps, ms_per_step=ms, higher_is_better=True, scaling="strong" if total_batch is not None else "weak",
@@ -522,13 +531,16 @@ def run_codec(args, cfg, ctx, collect_secondary):
     e2e_split = dict(h2d_ms=ev[0].elapsed_time(ev[1]), compute_ms=ev[1].elapsed_time(ev[2]), d2h_ms=ev[2].elapsed_time(ev[3]),
                      note="one extra step, serial on the launching stream (no overlap between copies and kernels)")
 
-    # ---- roofline of the dominant kernel: the ConvNeXt pointwise GEMM (tcgen05), timed alone
+    # ---- roofline of the dominant kernel: the ConvNeXt pointwise GEMM (tcgen05), timed alone on operands of the step's shapes
     M, C, I = B * F_, 1536, 4608
-    blk = model._prepare()["enc"]["convnext"][0]
-    t1 = model._planes("cnx_t1", (M, C), model.policy["convnext"])
-    hid = model._planes("cnx_hid", (M, I), model.policy["convnext"])
+    sd_ = model.state_dict()
+    w1 = ops.Planes.from_f32(sd_["encoder.prior_net.0.pwconv1.linear.weight"], False)
+    b1 = sd_["encoder.prior_net.0.pwconv1.linear.bias"].float().contiguous()
+    t1 = ops.Planes(torch.randn(M, C, device=dev).half(), None)
+    hid = ops.Planes.zeros((M, I), False, dev)
     reps = 10
-    run1 = lambda: model._linear(t1, blk["w1"], I, M, C, bias=blk["b1"], act=ops.ACT_GELU, out_planes=hid, out_planes_map=(I, M, 0))
+    run1 = lambda: ops.gemm(t1, w1, I, a_batch=1, a_rows_per_batch=M, a_ld=C, m_per_batch=M, bias=b1, act=ops.ACT_GELU,
+                            out_planes=hid, out_planes_map=(I, M, 0))
     for _ in range(3):
         run1()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -540,6 +552,7 @@ def run_codec(args, cfg, ctx, collect_secondary):
     torch.cuda.synchronize()
     gemm_ms = e0.elapsed_time(e1) / reps
     gemm_tf = 2.0 * M * I * C / (gemm_ms * 1e-3) / 1e12
+    del t1, hid, w1
 
     samples = world * B * T
     value = samples / (ms * 1e-3)
@@ -606,7 +619,7 @@ def run_codec(args, cfg, ctx, collect_secondary):
         if world == 1 and args.precision != "accurate":
             try:        # fp32-grade policy (every GEMM a 3-term split) beside the default
                 del graphed
-                model._ws = {}
+                model._ws, model._engine = {}, None
                 torch.cuda.empty_cache()
                 macc = build_codec(cfg, dev, "accurate")
                 gacc = macc.graphed("roundtrip", wav_d, feat_d)

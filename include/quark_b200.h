@@ -281,6 +281,104 @@ int qb_lm_head_sample_tc(const float* x, int64_t B, int32_t hidden, const qb_hal
                          int32_t* pos, int32_t* slot, float* part_val, int32_t* part_idx, float* logits,
                          float temperature, int32_t top_k, float top_p, const uint32_t* seed, float* debug, void* stream);
 
+/* ==========================================================================================================
+ * Handle-level contract: what a non-Python caller binds.  A handle owns its repacked weight arena,
+ * workspace, KV cache and per-device context; every tensor argument is a caller-owned DEVICE pointer (row-major,
+ * contiguous, 16-byte aligned); calls are stream-ordered and asynchronous, return 0 / negative, and never synchronise
+ * the device after `*_load`.  A handle is bound to the device current at creation and is not thread-safe.
+ * The op-level entry points above are what these are built from (csrc/engine.cu); the Python faces
+ * (unified_audio_b200/codec.py, llm.py) call these for the product path.
+ * ========================================================================================================== */
+typedef struct qb_handle qb_handle;   /* per-device context */
+typedef struct qb_codec qb_codec;     /* H-Codec-2.0 model: weights + workspace */
+typedef struct qb_rvq qb_rvq;         /* one residual vector quantiser (codebooks + search constants) */
+typedef struct qb_lm qb_lm;           /* UniSE AR-LM: weights + workspace */
+typedef struct qb_kv qb_kv;           /* static fp32 KV cache + device-side decode state of one batch */
+
+/* A named fp32 tensor of the reference's state-dict (device pointer, contiguous). */
+typedef struct {
+  const char* name;      /* e.g. "encoder.prior_net.0.pwconv1.linear.weight" */
+  const float* data;
+  int32_t ndim;
+  int64_t shape[4];
+} qb_tensor;
+
+enum { QB_PRECISION_MIXED = 0, QB_PRECISION_ACCURATE = 1, QB_PRECISION_FAST = 2, QB_PRECISION_MIXED_DEC16 = 3 };
+
+/* H-Codec-2.0 hyper-parameters (QuarkAudio-HCodec/HCodec-2.0/conf/large_12.5hz_config.yaml; vq/codec.py:18-49). */
+typedef struct {
+  int32_t dim, intermediate_dim, dimension;          /* encoder/decoder width 1536, ConvNeXt hidden 4608, latent 512 */
+  int32_t n_fft, hop_length;                         /* 1920 / 960 (n_fft == 2*hop required) */
+  int32_t enc_convnext_layers, enc_transformer_layers;
+  int32_t dec_convnext_layers, dec_transformer_layers;
+  int32_t dec_input_channels;                        /* 2 * dimension */
+  int32_t frame_stride;                              /* 50 Hz frames per token = 50 / target_frame_rate (4) */
+  int32_t num_quantizers, codebook_size;
+  int32_t sem_input_channels, sem_encode_channels, sem_out_channels;
+  int32_t sem_n_blocks;
+  int32_t sem_strides[8];
+  int32_t precision;                                 /* QB_PRECISION_* (DESIGN.md "precision policy") */
+} qb_codec_cfg;
+
+int qb_init(int device, qb_handle** out);
+/* stream-ordered device-to-device copy (lets a tap callback written in a language without a CUDA binding keep a buffer) */
+int qb_memcpy_d2d(void* dst, const void* src, int64_t bytes, void* stream);
+void qb_handle_free(qb_handle* h);
+/* last error of this thread's most recent failing call (same buffer as qb_last_error()) */
+const char* qb_handle_last_error(qb_handle* h);
+
+/* Builds the model from the reference's state-dict tensors (names as `Codec.state_dict()` gives them: `encoder.*`,
+ * `decoder.*`, `semantic_encoder.*`, `quantizer.layers.{i}._codebook.embed`, `semantic_quantizer...`): repacks every weight
+ * once (fp16 planes, conv taps, interleaved SwiGLU rows, LSTM unit-major slices, DFT matrices in fp64).  Synchronous.
+ * Replaces Codec.__init__ + load_state_dict (vq/codec.py:18-49, audio_tokenizer.py:27-35). */
+int qb_codec_load(qb_handle* h, const qb_codec_cfg* cfg, const qb_tensor* named_weights, int32_t n, qb_codec** out);
+void qb_codec_free(qb_codec* c);
+/* Codec.encode (vq/codec.py:75-87): wav [B,T] fp32 (T a multiple of hop*frame_stride), feat [B,768,T/hop] fp32 ->
+ * acoustic / semantic codes int64 [B, nq, N], N = T / (hop*frame_stride). */
+int qb_codec_encode(qb_codec* c, const float* wav, int64_t B, int64_t T, const float* feat, int64_t* ac_codes,
+                    int64_t* sem_codes, void* stream);
+/* Codec.decode (vq/codec.py:89-99): codes int64 [B, nq, N] x2 -> wav [B, N*hop*frame_stride] fp32. */
+int qb_codec_decode(qb_codec* c, const int64_t* ac_codes, const int64_t* sem_codes, int64_t B, int64_t N, float* wav,
+                    void* stream);
+/* Debug taps: when set, the engine calls `cb(user, name, dev_ptr, B, rows, C)` right after enqueueing the kernels that produce
+ * the named intermediate ([B, rows, C] fp32, channel-last); the callee may enqueue a copy on the same stream.  NULL disables. */
+typedef void (*qb_tap_fn)(void* user, const char* name, const float* data, int64_t B, int64_t rows, int64_t C);
+int qb_codec_set_tap(qb_codec* c, qb_tap_fn cb, void* user);
+/* Row-level access to the two quantisers of a loaded codec (which = 0 acoustic, 1 semantic). */
+qb_rvq* qb_codec_rvq(qb_codec* c, int32_t which);
+
+/* ResidualVQ (third-party vector_quantize_pytorch; call sites vq/codec.py:81-82,94-95): codebooks [nq, K, D] fp32. */
+int qb_rvq_load(qb_handle* h, const float* codebooks, int32_t nq, int32_t K, int32_t D, qb_rvq** out);
+void qb_rvq_free(qb_rvq* q);
+/* x [M, D] fp32 -> idx [M, nq] int64 (+ quantized [M, D] or NULL) */
+int qb_rvq_encode_rows(qb_rvq* q, const float* x, int64_t M, int64_t* idx, float* quantized_or_null, void* stream);
+/* idx [M, nq] int64 -> out [M, D] fp32 (sum over layers, q = 0..nq-1 in order) */
+int qb_rvq_decode_rows(qb_rvq* q, const int64_t* idx, int64_t M, float* out, void* stream);
+
+/* UniSE AR-LM hyper-parameters (QuarkAudio-UniSE/conf/config.yaml:138-146; model/llm/llm.py:40-83). */
+typedef struct {
+  int32_t hidden, layers, heads, inter;       /* 512, 12, 8, 2048 (head_dim 64 required) */
+  int32_t vocab;                              /* 3 + global_size + semantic_size = 12291 */
+  int32_t max_positions;                      /* RoPE table rows allocated at load (grown by the caller via a reload) */
+} qb_lm_cfg;
+/* named weights: `layers.{i}.self_attn.{q,k,v,o}_proj.weight`, `layers.{i}.mlp.{gate,up,down}_proj.weight`,
+ * `layers.{i}.{input,post_attention}_layernorm.weight`, `norm.weight`, `codec_embedding.weight`, `output_head.weight`. */
+int qb_lm_load(qb_handle* h, const qb_lm_cfg* cfg, const qb_tensor* named_weights, int32_t n, qb_lm** out);
+void qb_lm_free(qb_lm* m);
+int qb_kv_alloc(qb_lm* m, int64_t B, int32_t Lmax, qb_kv** out);
+void qb_kv_free(qb_kv* kv);
+int qb_kv_reset(qb_kv* kv, void* stream);
+/* CustomLlamaModel.llm_forward on a prefix (llm.py:150-228; llm_sft.py:130-135): embeds [B,P,hidden] appended to the
+ * cache at its current length; last_hidden [B,P,hidden] = final-RMSNorm output (may be NULL). */
+int qb_lm_prefill(qb_lm* m, const float* embeds, int64_t B, int64_t P, qb_kv* kv, float* last_hidden, void* stream);
+/* n_steps cached greedy steps (llm_sft.py:137-193 with do_sample=False): starts from token `first_token`'s embedding,
+ * each step restricts the head to columns [col_lo, col_hi) and feeds the arg-max back; out_ids [B, n_steps] int64 (raw
+ * vocabulary ids).  B <= 32. */
+int qb_lm_decode_greedy(qb_lm* m, qb_kv* kv, int64_t B, int32_t first_token, int32_t n_steps, int32_t col_lo,
+                        int32_t col_hi, int64_t* out_ids, void* stream);
+/* Teacher-forced logits (llm_sft.py:81-86): embeds [B,L,hidden] -> logits [B,L,vocab] fp32 (fresh context, no cache kept). */
+int qb_lm_forward_logits(qb_lm* m, const float* embeds, int64_t B, int64_t L, float* logits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,3 +93,22 @@ def feat_tap_error(a, b, verbose=True):
               f"raw log max-rel {rel(la, lb):.2e} at a bin of magnitude {float(mb.flatten()[i]):.2e} (max {float(mb.max()):.2e}); "
               f"bins at the 1e-5 clip floor: {int((mb <= 1.0001e-5).sum())}")
     return max(e_mag, e_log, e_ph)
+
+
+def phase_wrap_clips(a, b):
+    """STFT feature taps [B, 2*nf, F] (ours, oracle) -> (bool [B]: clips where some phase channel differs by a full turn,
+    number of wrapped bins, worst on-circle phase difference at the wrapped bins).
+
+    The reference's feature angle(S)/pi (vq/codec_encoder.py:70) has a branch cut at +-1: a bin whose spectrum has re < 0 and
+    |im| within the float noise of the FFT (about 1e-6 of the frame's largest magnitude - the reference's own fp32 FFT is that
+    far from exact arithmetic) lands on +1 or -1 by the sign of a rounding error.  About one bin in a million does; any
+    implementation whose FFT is not bit-identical to the reference's (the reference itself on cuFFT vs its CPU FFT included)
+    flips some of them, and a flipped channel moves the embed convolution's input by 2.0, i.e. the whole clip by ~1e-2
+    downstream.  Such clips are checked ON THE CIRCLE (the feature is right, the function is discontinuous) and excluded
+    from the 1e-3 assertions - the count is reported."""
+    nf = b.shape[1] // 2
+    d = a[:, nf:].double() - b[:, nf:].double()
+    wrapped = d.abs() > 1.0
+    circ = ((d + 1) % 2 - 1).abs()
+    worst = float(circ[wrapped].max()) if bool(wrapped.any()) else 0.0
+    return wrapped.flatten(1).any(1), int(wrapped.sum()), worst

@@ -11,7 +11,7 @@ import os
 import pytest
 import torch
 
-from oracle.parity import audit_codes, feat_tap_error, l2, rel
+from oracle.parity import audit_codes, feat_tap_error, l2, phase_wrap_clips, rel
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3          # north_star: floats within 1e-3 relative
@@ -91,37 +91,50 @@ def test_h2_index_identity_full_batch(lib):
         torch.set_num_threads(min(32, len(os.sched_getaffinity(0))))
     except Exception:
         pass
-    otaps, gtaps = {}, {}
+    gtaps = {}
     oa, os_ = [], []
     chunk = 8
-    oemb, osem = [], []
+    oemb, osem, ofeat = [], [], []
     for i in range(0, clips, chunk):              # the oracle in chunks (bounded host memory)
         t = {}
         a, s = hcodec2.codec_encode(sd, cfg, wav[i:i + chunk], feat[i:i + chunk], taps=t)
-        oa.append(a); os_.append(s); oemb.append(t["enc.out"]); osem.append(t["sem.out"])
-    oa, os_, oemb, osem = torch.cat(oa), torch.cat(os_), torch.cat(oemb), torch.cat(osem)
+        oa.append(a); os_.append(s); oemb.append(t["enc.out"]); osem.append(t["sem.out"]); ofeat.append(t["enc.feat"])
+    oa, os_, oemb, osem, ofeat = torch.cat(oa), torch.cat(os_), torch.cat(oemb), torch.cat(osem), torch.cat(ofeat)
     ac, sc = model.encode(wav.cuda(), feat.cuda(), taps=gtaps)
     torch.cuda.synchronize()
     B, D, N = oemb.shape
-    rows = lambda t: t.float().cpu().transpose(1, 2).reshape(B * N, D)
-    e_emb, e_sem = rel(gtaps["enc.out"], oemb), rel(gtaps["sem.out"], osem)
-    print(f"[index identity, {clips} clips] emb rel {e_emb:.2e} sem rel {e_sem:.2e}")
+    # clips with a phase bin on the angle() branch cut (oracle/parity.py::phase_wrap_clips): checked on the circle, reported, and
+    # excluded from the float-tolerance assertions below
+    cut, n_wrapped, worst_circ = phase_wrap_clips(gtaps["enc.feat"].float().cpu(), ofeat)
+    ok = ~cut
+    print(f"[index identity, {clips} clips] {int(cut.sum())} clip(s) have a phase bin on the branch cut ({n_wrapped} of "
+          f"{ofeat.shape[0] * (ofeat.shape[1] // 2) * ofeat.shape[2]} bins; on-circle difference there {worst_circ:.1e}): {cut.nonzero().flatten().tolist()}")
+    assert worst_circ < 1e-3 and int(cut.sum()) <= max(1, clips // 3)
+    assert feat_tap_error(gtaps["enc.feat"].float().cpu()[ok], ofeat[ok]) < TOL
+    rows = lambda t: t.float().cpu()[ok].transpose(1, 2).reshape(-1, D)
+    e_emb, e_sem = rel(gtaps["enc.out"].float().cpu()[ok], oemb[ok]), rel(gtaps["sem.out"], osem)
+    e_cut = rel(gtaps["enc.out"].float().cpu()[cut], oemb[cut]) if bool(cut.any()) else 0.0
+    print(f"[index identity, {clips} clips] emb rel {e_emb:.2e} (branch-cut clips: {e_cut:.2e}) sem rel {e_sem:.2e}")
     assert e_emb < TOL and e_sem < TOL
     for tag, got, want, g, o, q in (("acoustic", ac, oa, gtaps["enc.out"], oemb, "quantizer"),
                                     ("semantic", sc, os_, gtaps["sem.out"], osem, "semantic_quantizer")):
         cb = hcodec2._codebooks(sd, q)
-        a = audit_codes(got, want, rows(g), rows(o), cb)
+        a = audit_codes(got[ok.to(got.device)], want[ok], rows(g), rows(o), cb)
         print(f"[index identity] {tag}: {a}")
-        assert a["tokens"] == clips * 125 and a["explained"], f"{tag}: unexplained index difference {a}"
-        # RVQ kernel alone on the ORACLE's embedding: bit-exact on every one of the clips*125*16 decisions
-        idx, _ = model.quantizer.encode_rows(rows(o).cuda()) if q == "quantizer" else model.semantic_quantizer.encode_rows(rows(o).cuda())
+        assert a["tokens"] == int(ok.sum()) * 125 and a["explained"], f"{tag}: unexplained index difference {a}"
+        # RVQ kernel alone on the ORACLE's embedding: bit-exact on every one of the clips*125*16 decisions (all clips)
+        allrows = o.float().transpose(1, 2).reshape(B * N, D)
+        qz = model.engine().rvq(0 if q == "quantizer" else 1) if model._use_engine() else (model.quantizer if q == "quantizer" else model.semantic_quantizer)
+        idx, _ = qz.encode_rows(allrows.cuda())
         same = torch.equal(idx.cpu().reshape(B, N, -1).transpose(1, 2), want)
         if not same:
             from oracle import rvq
-            _, margin = rvq.rvq_margin_audit(rows(o), cb, want.transpose(1, 2).reshape(B * N, -1))
+            _, margin = rvq.rvq_margin_audit(allrows, cb, want.transpose(1, 2).reshape(B * N, -1))
             diff = (idx.cpu() != want.transpose(1, 2).reshape(B * N, -1))
             print(f"   rvq-on-oracle-embedding differences: {int(diff.sum())}, their fp64 rel margins {margin[diff][:8].tolist()}")
             assert float(margin[diff].max()) < 1e-6, "RVQ kernel differs from the oracle on identical inputs at a safe margin"
+        else:
+            print(f"   RVQ kernel on the oracle's embedding: all {B * N * idx.shape[1]} indices identical")
     # decode of the oracle's codes at the full batch: compare 4 clips' waveforms with the oracle
     rec = model.decode(oa.cuda(), os_.cuda())
     torch.cuda.synchronize()

@@ -28,6 +28,25 @@ class GemmDesc(C.Structure):
     ]
 
 
+class Tensor(C.Structure):       # qb_tensor
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
+
+
+class CodecCfg(C.Structure):     # qb_codec_cfg
+    _fields_ = [(n, C.c_int32) for n in (
+        "dim", "intermediate_dim", "dimension", "n_fft", "hop_length", "enc_convnext_layers", "enc_transformer_layers",
+        "dec_convnext_layers", "dec_transformer_layers", "dec_input_channels", "frame_stride", "num_quantizers", "codebook_size",
+        "sem_input_channels", "sem_encode_channels", "sem_out_channels", "sem_n_blocks")] + [("sem_strides", C.c_int32 * 8),
+                                                                                             ("precision", C.c_int32)]
+
+
+class LmCfg(C.Structure):        # qb_lm_cfg
+    _fields_ = [(n, C.c_int32) for n in ("hidden", "layers", "heads", "inter", "vocab", "max_positions")]
+
+
+TAP_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64)
+PRECISION_CODES = {"mixed": 0, "accurate": 1, "fast": 2, "mixed_dec16": 3}
+
 # name -> (restype, argtypes); mirrors include/quark_b200.h one to one
 _vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 SIGNATURES = {
@@ -78,6 +97,28 @@ SIGNATURES = {
     "qb_lm_decode_layer_tc": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp]),
     "qb_lm_head_argmax_tc": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "qb_init": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "qb_handle_free": (None, [_vp]),
+    "qb_memcpy_d2d": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "qb_handle_last_error": (C.c_char_p, [_vp]),
+    "qb_codec_load": (C.c_int, [_vp, C.POINTER(CodecCfg), C.POINTER(Tensor), _i32, C.POINTER(_vp)]),
+    "qb_codec_free": (None, [_vp]),
+    "qb_codec_encode": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "qb_codec_decode": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "qb_codec_set_tap": (C.c_int, [_vp, TAP_FN, _vp]),
+    "qb_codec_rvq": (_vp, [_vp, _i32]),
+    "qb_rvq_load": (C.c_int, [_vp, _vp, _i32, _i32, _i32, C.POINTER(_vp)]),
+    "qb_rvq_free": (None, [_vp]),
+    "qb_rvq_encode_rows": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "qb_rvq_decode_rows": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "qb_lm_load": (C.c_int, [_vp, C.POINTER(LmCfg), C.POINTER(Tensor), _i32, C.POINTER(_vp)]),
+    "qb_lm_free": (None, [_vp]),
+    "qb_kv_alloc": (C.c_int, [_vp, _i64, _i32, C.POINTER(_vp)]),
+    "qb_kv_free": (None, [_vp]),
+    "qb_kv_reset": (C.c_int, [_vp, _vp]),
+    "qb_lm_prefill": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "qb_lm_decode_greedy": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "qb_lm_forward_logits": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "qb_lm_head_sample_tc": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _i32,
                                        _f32, _vp, _vp, _vp]),
 }

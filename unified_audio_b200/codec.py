@@ -14,6 +14,7 @@ pass).  There is no PyTorch / CPU fallback.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -73,20 +74,41 @@ class Codec(nn.Module):
         self.semantic_quantizer = ResidualVQ(**quantizer_kwargs)
         self.semantic_encoder = _Tree.build(spec.semantic_encoder_spec(**semantic_encoder_kwargs))
         self.policy = dict(PRECISION_POLICIES[precision])
-        self._w = None        # repacked weights (device planes)
+        self._w = None        # repacked weights (device planes) of the Python-orchestrated path
         self._ws = {}         # workspace cache
+        self.precision = precision
+        # "c" (default): encode / decode are ONE call each into the handle-level C ABI (csrc/engine.cu owns the weight arena, the
+        # workspace and the ~340-kernel orchestration).  "python": the same kernels launched op by op from this file - kept as the
+        # cross-check of the engine (tests/test_engine_gpu.py) and as the base CodecH1 builds on.
+        self.engine_mode = os.environ.get("QB_CODEC_ENGINE", "c")
+        self._engine = None
         self.eval()
 
     # ------------------------------------------------------------------ state handling
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         sd = {k: v for k, v in state_dict.items() if not k.startswith("semantic_decoder.")}
         r = super().load_state_dict(sd, strict=strict, assign=assign)
-        self._w = None
+        self._w, self._engine = None, None
         return r
 
     def _apply(self, fn, *a, **k):
-        self._w, self._ws = None, {}
+        self._w, self._ws, self._engine = None, {}, None
         return super()._apply(fn, *a, **k)
+
+    def _use_engine(self) -> bool:
+        return self.engine_mode == "c" and type(self) is Codec
+
+    def engine(self):
+        """The qb_codec handle of this model (built lazily from the current parameters)."""
+        if self._engine is None:
+            from .engine import CodecEngine
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("unified_audio_b200.Codec runs on CUDA only (no CPU fallback): call .cuda() first")
+            self._engine = CodecEngine(dev, self.enc_cfg, self.dec_cfg, dict(num_quantizers=self.quantizer.num_quantizers,
+                                                                             codebook_size=self.quantizer.codebook_size),
+                                       self.sem_cfg, self.precision, {k: v for k, v in self.state_dict().items()})
+        return self._engine
 
     # ------------------------------------------------------------------ weight repack (load time)
     def _prepare(self):
@@ -465,6 +487,15 @@ class Codec(nn.Module):
     @torch.no_grad()
     def encode(self, x, feat, taps=None):
         """vq/codec.py:75-87: x [B,T] fp32, feat [B,768,T/960] fp32 -> (acoustic, semantic) int64 [B,nq,N]."""
+        if self._use_engine():
+            eng = self.engine()
+            if taps is None:
+                return eng.encode(x, feat)
+            eng.set_taps(taps)
+            try:
+                return eng.encode(x, feat)
+            finally:
+                eng.set_taps(None)
         emb, N = self._encode_emb(x, taps)
         sem, Ns = self._encode_sem(feat, taps)
         if Ns != N:
@@ -477,6 +508,15 @@ class Codec(nn.Module):
     @torch.no_grad()
     def decode(self, acoustic_codes, semantic_codes, taps=None):
         """vq/codec.py:89-99: int64 [B,nq,N] x2 -> wav [B, N*3840]."""
+        if self._use_engine():
+            eng = self.engine()
+            if taps is None:
+                return eng.decode(acoustic_codes, semantic_codes)
+            eng.set_taps(taps)
+            try:
+                return eng.decode(acoustic_codes, semantic_codes)
+            finally:
+                eng.set_taps(None)
         B, nq, N = acoustic_codes.shape
         Dq = self.quantizer.dim
         z = self._buf("dec_z", (B * N, 2 * Dq))

@@ -201,6 +201,22 @@ __device__ __forceinline__ void tma2_load_3d(void* smem_dst, const void* tmap, u
       ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(bar_cluster_addr), "r"(x), "r"(y), "r"(z)
       : "memory");
 }
+// multicast variants: the box lands at the same smem offset in every CTA of `mask`; each destination's completion bytes are
+// signalled on the barrier at the same offset in that destination's PAIR LEADER (peer bit 24 of the shared::cluster address
+// cleared - the CUTLASS SM100_TMA_2SM_LOAD_MULTICAST convention)
+__device__ __forceinline__ void tma2_load_2d_mc(void* smem_dst, const void* tmap, uint64_t* bar, int x, int y, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(x), "r"(y), "h"(mask)
+      : "memory");
+}
+// same address convention for a non-multicast load of a pair inside a larger cluster
+__device__ __forceinline__ void tma2_load_3d_peer(void* smem_dst, const void* tmap, uint64_t* bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)
                : "memory");

@@ -506,6 +506,142 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------ two CTA pairs per cluster, weight tile multicast
+// The pair kernel above is bound by the bytes the L2 can deliver per SM (measured 40 B/clk/SM = the chip-level
+// 6.3 kB/clk cap, profiles/r01_ncu_gemm_pair_final.txt): per K-block every CTA pulls A 16 KB + W 16 KB for 512 MMA cycles.
+// Here a cluster of FOUR CTAs = two pairs owns a 512 x BN super-tile: the pairs take adjacent 256-row M tiles of the SAME
+// N tile, so the CTAs with equal pair rank need the same half of the weight tile - each loads a quarter (64 rows) and
+// multicasts it to its counterpart.  L2 -> SM requests per CTA and K-block: 16 + 8 = 24 KB (48 B/clk at full tensor rate).
+// Protocol: full[]: as the pair kernel (all bytes that land in a pair's two CTAs are signalled on that pair's leader);
+// empty[]: a stage of CTA c is also written by its counterpart, so BOTH leaders' commits arrive on every CTA's empty
+// barrier (count 2); tfull / tempty stay pair-local.  a_batch == 1 only (nn.Linear shapes); rows past M are zero-filled
+// by TMA and masked in the epilogue, so an odd number of pair tiles needs no special case.
+template <int BN, int NTERMS, int STAGES>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                const GemmParams p) {
+  constexpr int BM = 128, BK = 64;
+  constexpr int NPL = (NTERMS == 1) ? 1 : 2;
+  constexpr uint32_t A_BYTES = BM * BK * 2, W_BYTES = (BN / 2) * BK * 2, WQ_BYTES = W_BYTES / 2;
+  constexpr uint32_t STAGE_BYTES = NPL * (A_BYTES + W_BYTES);
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two <= 512");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank(), pair = rank >> 1, r = rank & 1;
+  const bool leader = r == 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * GEMM_EPI_WARPS); }
+    fence_mbar_init();
+  }
+  if (warp == GEMM_EPI_WARPS + 1) { tmem_alloc2(tmem_slot, TMEM_COLS); tmem_relinquish2(); }
+  if (warp == GEMM_EPI_WARPS && lane == 0) {
+    prefetch_tmap(&tmA_hi); prefetch_tmap(&tmW_hi);
+    if (NPL == 2) { prefetch_tmap(&tmA_lo); prefetch_tmap(&tmW_lo); }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_clusters = gridDim.x >> 2, cluster_id = blockIdx.x >> 2;
+  const int num_super = p.tiles_per_batch * p.num_n_tiles;       // tiles_per_batch = ceil(M / 512) here
+
+  if (warp == GEMM_EPI_WARPS) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint16_t mc_mask = (uint16_t)((1u << r) | (1u << (2 + r)));
+      for (int tile = cluster_id; tile < num_super; tile += num_clusters) {
+        const int n_tile = tile % p.num_n_tiles, m_super = tile / p.num_n_tiles;
+        const int m0 = (m_super * 2 + (int)pair) * 2 * BM + (int)r * BM;
+        const int n0 = n_tile * BN + (int)r * (BN / 2) + (int)pair * (BN / 4);      // this CTA's quarter of the weight tile
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+          uint8_t* s = smem + stage * STAGE_BYTES;
+          const int kx = kb * BK;
+          tma2_load_3d_peer(s, &tmA_hi, &full[stage], kx, m0, 0);
+          if (NPL == 2) tma2_load_3d_peer(s + A_BYTES, &tmA_lo, &full[stage], kx, m0, 0);
+          tma2_load_2d_mc(s + NPL * A_BYTES + pair * WQ_BYTES, &tmW_hi, &full[stage], kx, n0, mc_mask);
+          if (NPL == 2) tma2_load_2d_mc(s + NPL * A_BYTES + W_BYTES + pair * WQ_BYTES, &tmW_lo, &full[stage], kx, n0, mc_mask);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == GEMM_EPI_WARPS + 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_f16(2 * BM, BN);
+      const uint16_t pair_mask = (uint16_t)(3u << (2 * pair));
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int tile = cluster_id; tile < num_super; tile += num_clusters, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t a_hi = make_sw128_kmajor_desc(sa + k * 32);
+            const uint64_t w_hi = make_sw128_kmajor_desc(sa + NPL * A_BYTES + k * 32);
+            umma2_f16(d_tmem, a_hi, w_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (NTERMS == 3) {
+              const uint64_t a_lo = make_sw128_kmajor_desc(sa + A_BYTES + k * 32);
+              const uint64_t w_lo = make_sw128_kmajor_desc(sa + NPL * A_BYTES + W_BYTES + k * 32);
+              umma2_f16(d_tmem, a_lo, w_hi, idesc, 1u);
+              umma2_f16(d_tmem, a_hi, w_lo, idesc, 1u);
+            }
+          }
+          umma2_commit_mc(&empty[stage], 0xF);          // the stage is free once BOTH pairs have consumed it
+          if (kb == p.num_kb - 1) umma2_commit_mc(&tfull[acc], pair_mask);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    constexpr int CPW = BN / (GEMM_EPI_WARPS / 4);
+    const int q = warp & 3, hc = warp >> 2;
+    uint32_t it = 0;
+    const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty[0]), rank & ~1u);
+    for (int tile = cluster_id; tile < num_super; tile += num_clusters, ++it) {
+      const int n_tile = tile % p.num_n_tiles, m_super = tile / p.num_n_tiles;
+      const int m0 = (m_super * 2 + (int)pair) * 2 * BM + (int)r * BM, n0 = n_tile * BN;
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + hc * CPW;
+#pragma unroll 1
+      for (int c = 0; c < CPW; c += 32) {
+        uint32_t rr[32];
+        tmem_ld_32x32b_x32(taddr + c, rr);
+        tmem_ld_wait();
+        epilogue_row32(p, 0, m0 + q * 32 + lane, n0 + hc * CPW + c, rr);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader + acc * 8);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == GEMM_EPI_WARPS + 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------ SIMT cross-check
 __global__ void gemm_simt_kernel(const GemmParams p) {
   const int N_out = p.act == QB_ACT_SWIGLU ? p.N / 2 : p.N;
@@ -684,6 +820,57 @@ static int launch_tc2(const qb_gemm_desc* d, cudaStream_t st, int num_sms) {
   return 0;
 }
 
+
+template <int BN, int NTERMS, int STAGES>
+static int launch_tc4(const qb_gemm_desc* d, cudaStream_t st, int num_sms) {
+  GemmParams p;
+  if (int e = fill_params(d, &p, BN)) return e;
+  QB_REQUIRE(d->a_batch == 1 && d->taps == 1 && d->stride == 1, "gemm: the 4-CTA multicast kernel serves plain linear layers only");
+  p.tiles_per_batch = (int)ceil_div(d->m_per_batch, 512);      // super-tiles of 2 x 256 rows
+  p.num_tiles = p.tiles_per_batch * p.num_n_tiles;
+  CUtensorMap mA_hi, mA_lo, mW_hi, mW_lo;
+  const cuuint64_t C = (cuuint64_t)d->a_ld;
+  cuuint64_t adims[3] = {C, (cuuint64_t)d->a_rows_per_batch, 1};
+  cuuint64_t astr[2] = {C * 2, (cuuint64_t)d->a_rows_per_batch * C * 2};
+  cuuint32_t abox[3] = {64, 128, 1};
+  cuuint64_t wdims[2] = {C, (cuuint64_t)d->n};
+  cuuint64_t wstr[1] = {C * 2};
+  cuuint32_t wbox[2] = {64, (cuuint32_t)(BN / 4)};
+  if (int e = make_map(&mA_hi, d->a_hi, 3, adims, astr, abox)) return e;
+  if (int e = make_map(&mW_hi, d->w_hi, 2, wdims, wstr, wbox)) return e;
+  if (NTERMS == 3) {
+    if (int e = make_map(&mA_lo, d->a_lo, 3, adims, astr, abox)) return e;
+    if (int e = make_map(&mW_lo, d->w_lo, 2, wdims, wstr, wbox)) return e;
+  } else {
+    mA_lo = mA_hi; mW_lo = mW_hi;
+  }
+  constexpr int NPL = NTERMS == 1 ? 1 : 2;
+  constexpr size_t smem = (size_t)STAGES * NPL * (128 * 64 * 2 + (BN / 2) * 64 * 2) + 1024 + 256;
+  auto kern = gemm_tc4_kernel<BN, NTERMS, STAGES>;
+  static int max_clusters[QB_MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (!max_clusters[dev]) {
+    QB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * 64); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    QB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    QB_REQUIRE(n >= 1, "gemm: no 4-CTA cluster fits on this device");
+    if (const char* e = getenv("QB_GEMM4_CLUSTERS")) n = atoi(e) < n ? atoi(e) : n;
+    max_clusters[dev] = n;
+  }
+  (void)num_sms;
+  int clusters = p.num_tiles < max_clusters[dev] ? p.num_tiles : max_clusters[dev];
+  kern<<<4 * clusters, GEMM_THREADS, smem, st>>>(mA_hi, mA_lo, mW_hi, mW_lo, p);
+  g_launches++;
+  QB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static int num_sms_cached() {
   static int n[QB_MAX_DEVICES] = {};
   const int dev = current_device();
@@ -704,8 +891,14 @@ extern "C" int64_t qb_launch_count(void) { return (int64_t)g_launches.load(); }
 extern "C" void qb_launch_count_reset(void) { g_launches = 0; }
 
 // kernel variant for a problem shape (one place: qb_gemm dispatches on it, qb_gemm_kernel_name reports it)
-enum GemmVariant { GV_PAIR_SINGLE, GV_PAIR_SPLIT, GV_TC_256_SINGLE, GV_TC_128_SINGLE, GV_TC_256_SPLIT, GV_TC_128_SPLIT };
-static GemmVariant pick_variant(int64_t m_per_batch, int64_t n, bool split) {
+enum GemmVariant { GV_QUAD_SINGLE, GV_PAIR_SINGLE, GV_PAIR_SPLIT, GV_TC_256_SINGLE, GV_TC_128_SINGLE, GV_TC_256_SPLIT, GV_TC_128_SPLIT };
+// QB_GEMM_QUAD=1: single-pass linear layers with M >= 4096 rows and N a multiple of 256 go to the 4-CTA multicast kernel
+static int quad_mode() {
+  static const int v = getenv("QB_GEMM_QUAD") ? atoi(getenv("QB_GEMM_QUAD")) : 0;
+  return v;
+}
+static GemmVariant pick_variant(int64_t m_per_batch, int64_t n, bool split, bool linear = false) {
+  if (linear && !split && quad_mode() && m_per_batch >= 4096 && n % 256 == 0) return GV_QUAD_SINGLE;
   int bn = n > 128 ? 256 : 128;
   if (split) bn = 128;
   static const char* env_bn = getenv("QB_GEMM_BN_SPLIT");
@@ -724,7 +917,8 @@ static GemmVariant pick_variant(int64_t m_per_batch, int64_t n, bool split) {
 }
 
 extern "C" const char* qb_gemm_kernel_name(int64_t m_per_batch, int64_t n, int32_t split) {
-  switch (pick_variant(m_per_batch, n, split != 0)) {
+  switch (pick_variant(m_per_batch, n, split != 0, true)) {
+    case GV_QUAD_SINGLE: return "gemm_tc4_kernel<256,1,6> (2 x cta_group::2, weight tile multicast)";
     case GV_PAIR_SINGLE: return "gemm_tc2_kernel<256,1,6> (cta_group::2)";
     case GV_PAIR_SPLIT: return "gemm_tc2_kernel<256,3,3> (cta_group::2)";
     case GV_TC_256_SINGLE: return "gemm_tc_kernel<256,1,4>";
@@ -738,7 +932,9 @@ extern "C" int qb_gemm(const qb_gemm_desc* d, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   QB_REQUIRE(d != nullptr, "gemm: null desc");
   const int sms = num_sms_cached();
-  switch (pick_variant(d->m_per_batch, d->n, d->a_lo != nullptr)) {
+  const bool linear = d->a_batch == 1 && d->taps == 1 && d->stride == 1;
+  switch (pick_variant(d->m_per_batch, d->n, d->a_lo != nullptr, linear)) {
+    case GV_QUAD_SINGLE: return launch_tc4<256, 1, 6>(d, st, sms);
     case GV_PAIR_SINGLE: return launch_tc2<256, 1, 6>(d, st, sms);
     case GV_PAIR_SPLIT: return launch_tc2<256, 3, 3>(d, st, sms);
     case GV_TC_256_SINGLE: return launch_tc<256, 1, 4>(d, st, sms);
