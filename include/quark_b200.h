@@ -88,6 +88,9 @@ typedef struct {
   const float* act_param;   /* [n] per-column parameter of `act`  (QB_ACT_SNAKE: alpha) or NULL */
   const float* act2_param;  /* [n] per-column parameter of `act2` (QB_ACT_SNAKE on the plane output only: the fp32 output is
                              * the residual trunk, the planes are Snake(trunk) for the next convolution) or NULL */
+  int64_t a_cols;           /* channels contracted per tap (multiple of 64, <= a_ld); 0 = a_ld.  With a_hi / a_lo offset to a
+                             * channel group this is a GROUPED convolution over a [.., a_ld] buffer: W is [n, taps * a_cols]
+                             * (HuBERT / WavLM positional conv: k = 128, 16 groups, transformers modeling_hubert.py) */
 } qb_gemm_desc;
 
 /* tcgen05 / TMA / TMEM persistent GEMM (the product path). */
@@ -153,6 +156,19 @@ int qb_wav_to_hopblocks(const float* wav, int64_t B, int64_t T, int32_t hop, qb_
  * forced to +0 (vq/codec_encoder.py:68-71). */
 int qb_stft_post(const float* spec, int64_t ld_spec, int64_t B, int64_t frames, int32_t nf, qb_half* hi,
                  qb_half* lo, int64_t ld, int64_t rows_per_batch, int64_t row_off, void* stream);
+/* Two-stage STFT (n_fft = P*Q; P <= 64, Q <= 64): the same spectrum as the one-GEMM form above with MMA chains of 4 / 8
+ * instead of n_fft/16 - the tensor core truncates on every accumulate, and at K = 1920 that bias is 25x an fp32 FFT's error
+ * (csrc/elementwise.cu).   gather -> qb_gemm [.., 64] x W_A[2P, 64] -> twiddle -> qb_gemm [.., 128] x W_B[2*(nf/P+1), 128] -> post2.
+ * qb_stft_gather: planes [(B*F*Q), 64], row (clip, f, b) col a = pad(wav)[hop f + Q a + b] * window[Q a + b].
+ * qb_stft_twiddle: Y [(frames_total*Q), ldY] (cols 2 k1, 2 k1 + 1 = re, im) x twiddle[b*P + k1] = (cos, -sin)(2 pi k1 b / n_fft)
+ *   -> planes [(frames_total*P), 128] (cols b = re, Q + b = im).
+ * qb_stft_post2: as qb_stft_post with X[k] = row (clip, f, k % P), cols 2 (k / P), 2 (k / P) + 1 of X [.., ldX]. */
+int qb_stft_gather(const float* wav, int64_t B, int64_t T, int32_t hop, int32_t n_fft, int32_t P, int32_t Q, const float* window,
+                   qb_half* hi, qb_half* lo, void* stream);
+int qb_stft_twiddle(const float* Y, int64_t ldY, int64_t frames_total, int32_t P, int32_t Q, const float* twiddle, qb_half* hi,
+                    qb_half* lo, void* stream);
+int qb_stft_post2(const float* X, int64_t ldX, int64_t B, int64_t frames, int32_t nf, int32_t P, qb_half* hi, qb_half* lo, int64_t ld,
+                  int64_t rows_per_batch, int64_t row_off, void* stream);
 /* head output [M, ld_in] fp32 (mag | phase) -> planes [M, ld]: re = min(exp(mag),100)*cos(p),
  * im = ...*sin(p)   (vq/heads.py:55-65). */
 int qb_istft_pre(const float* head, int64_t ld_in, int64_t M, int32_t nf, qb_half* hi, qb_half* lo, int64_t ld,
@@ -280,6 +296,36 @@ int qb_lm_head_sample_tc(const float* x, int64_t B, int32_t hidden, const qb_hal
                          int32_t max_cols, const float* embedding, float* x_next, int64_t* out_ids, int32_t out_stride,
                          int32_t* pos, int32_t* slot, float* part_val, int32_t* part_idx, float* logits,
                          float temperature, int32_t top_k, float top_p, const uint32_t* seed, float* debug, void* stream);
+
+/* ---------------------------------------------------------------- SSL feature front ends + tokenizer glue
+ * HuBERT-base / WavLM-base-plus (transformers modeling_hubert / modeling_wavlm) as the reference drives them from
+ * HCodecTokenizer.extract_ssl_features (QuarkAudio-HCodec/HCodec-2.0/audio_tokenizer.py:47-61) and
+ * Model.extract_semantic_features (QuarkAudio-UniSE/model/model.py:38-51).  The dense contractions (Resample as a 2-tap
+ * Toeplitz GEMM, conv layers 1-6, projections, grouped positional conv via `a_cols`, attention, FFN) run on qb_gemm /
+ * qb_attention_hd / qb_layernorm; these entry points add what is not a contraction. */
+/* Feature-encoder layer 0: x [B, T_in] fp32 -> Conv1d(1, C, k, stride, bias=False) -> GroupNorm(C groups: per channel over
+ * time, eps) -> GELU(erf) -> planes of a channel-last buffer [B, rows_per_batch, ld].  y_scratch: [B, T0, C] fp32 with
+ * T0 = (T_in - k) / stride + 1; workspace: qb_ssl_conv0_workspace_bytes(B, T0, C). */
+int64_t qb_ssl_conv0_workspace_bytes(int64_t B, int64_t T0, int32_t C);
+int qb_ssl_conv0_gn_gelu(const float* x, int64_t B, int64_t T_in, const float* w, int32_t C, int32_t k, int32_t stride,
+                         const float* gn_w, const float* gn_b, float eps, float* y_scratch, void* workspace, qb_half* hi,
+                         qb_half* lo, int64_t ld, int64_t rows_per_batch, int64_t row_off, void* stream);
+/* WavLM-base-plus attention (transformers modeling_wavlm.WavLMAttention as UniSE drives it, U/model/model.py:30,38-51):
+ * gate[b, h, t] = ga (gb const_h - 1) + 2, (ga, gb) = sigmoid of the two 4-sums of Linear(head_dim -> 8)(x[b, t, head h]);
+ * qb_attention_relbias: softmax(q k^T / sqrt(d) + gate[b, h, i] * rel_table[h, (j - i) + T - 1]) v, no rotary embedding;
+ * qkv [B, T, 3*heads*64] fp32, rel_table [heads, 2T - 1] (bucketed relative-position embedding per distance), output planes. */
+int qb_wavlm_gate(const float* x, int64_t B, int64_t T, int32_t heads, int32_t head_dim, const float* w, const float* bias,
+                  const float* cst, float* gate, void* stream);
+int qb_attention_relbias(const float* qkv, int64_t B, int64_t T, int32_t heads, int32_t head_dim, const float* rel_table,
+                         const float* gate, qb_half* out_hi, qb_half* out_lo, void* stream);
+/* out = scale * x (accumulate == 0) or out += scale * x: the running mean over the 13 hidden states (audio_tokenizer.py:55). */
+int qb_axpy(const float* x, float scale, int64_t n, int32_t accumulate, float* out, void* stream);
+/* x [B, T, C] fp32 -> sign(x) * |x| ** power (audio_tokenizer.py:57-60; power <= 0: copy), written channel-first [B, C, T]
+ * (channel_first != 0: the layout Codec.encode takes) or channel-last. */
+int qb_ssl_compress(const float* x, int64_t B, int64_t T, int32_t C, float power, int32_t channel_first, float* out, void* stream);
+/* out[b, i] = x[b, i - left] (zero outside, or wrapped modulo T_in when wrap != 0): pad_wav (audio_tokenizer.py:63-66),
+ * F.pad(wavs, (160, 160)) (:51), wrap padding of UniSE segments (QuarkAudio-UniSE/model/model.py:175-181). */
+int qb_pad_wav(const float* x, int64_t B, int64_t T_in, int64_t left, int64_t T_out, int32_t wrap, float* out, void* stream);
 
 /* ==========================================================================================================
  * Handle-level contract: what a non-Python caller binds.  A handle owns its repacked weight arena,

@@ -172,7 +172,7 @@ def test_gemm_desc_struct_layout_matches_header():
     assert GemmDesc.taps.offset == 40 and GemmDesc.stride.offset == 44 and GemmDesc.m_per_batch.offset == 48
     assert GemmDesc.residual.offset == 96 and GemmDesc.act.offset == 128 and GemmDesc.out_f32.offset == 136
     assert GemmDesc.dilation.offset == 136 + 3 * 32 and GemmDesc.act_param.offset == 136 + 3 * 32 + 8
-    assert C.sizeof(GemmDesc) == 136 + 3 * 32 + 24
+    assert GemmDesc.a_cols.offset == 136 + 3 * 32 + 24 and C.sizeof(GemmDesc) == 136 + 3 * 32 + 32
 
 
 def test_bench_reference_arm_contract():

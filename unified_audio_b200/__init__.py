@@ -6,6 +6,9 @@ Public surface mirrors the reference (alibaba/unified-audio):
   LLM_SFT          <- QuarkAudio-UniSE/model/llm/llm_sft.py:13 (llm_forward / forward / generate)
   CodecH1          <- QuarkAudio-HCodec/HCodec-1.0/vq/codec.py:21   (encode / decode)
   BiCodec          <- QuarkAudio-UniSE/model/bicodec/bicodec.py:182 (detokenize)
+  SSLFrontEnd      <- HuBERT-base / WavLM-base-plus feature extraction as HCodecTokenizer.extract_ssl_features
+                      (HCodec-2.0/audio_tokenizer.py:47-61) and Model.extract_semantic_features (U/model/model.py:38-51) drive them
+  HCodecTokenizer  <- QuarkAudio-HCodec/HCodec-2.0/audio_tokenizer.py:21-79 (pad_wav / tokenize / detokenize)
 Kernels live in csrc/ behind the C ABI of include/quark_b200.h (lib/libquark_b200.so).
 """
 __version__ = "0.1.0"
@@ -15,3 +18,4 @@ from .codec_h1 import CodecH1  # noqa: E402,F401
 from .rvq import ResidualVQ  # noqa: E402,F401
 from .llm import LLM_SFT  # noqa: E402,F401
 from .bicodec import BiCodec  # noqa: E402,F401
+from .ssl import HCodecTokenizer, HUBERT_BASE, SSLFrontEnd, WAVLM_BASE_PLUS, pad_wav, wrap_segments  # noqa: E402,F401

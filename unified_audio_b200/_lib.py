@@ -25,6 +25,7 @@ class GemmDesc(C.Structure):
         ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("n", C.c_int64), ("bias", C.c_void_p), ("gamma", C.c_void_p),
         ("residual", RowMap), ("act", C.c_int32), ("act2", C.c_int32), ("out_f32", RowMap), ("out_hi", RowMap),
         ("out_lo", RowMap), ("dilation", C.c_int32), ("act_param", C.c_void_p), ("act2_param", C.c_void_p),
+        ("a_cols", C.c_int64),
     ]
 
 
@@ -72,6 +73,9 @@ SIGNATURES = {
                                       _i64, _vp]),
     "qb_wav_to_hopblocks": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp]),
     "qb_stft_post": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "qb_stft_gather": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "qb_stft_twiddle": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "qb_stft_post2": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _i64, _i64, _i64, _vp]),
     "qb_istft_pre": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _i64, _vp]),
     "qb_istft_ola": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     "qb_reflect_pad_rows": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _vp]),
@@ -97,6 +101,13 @@ SIGNATURES = {
     "qb_lm_decode_layer_tc": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp]),
     "qb_lm_head_argmax_tc": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "qb_ssl_conv0_workspace_bytes": (C.c_int64, [_i64, _i64, _i32]),
+    "qb_ssl_conv0_gn_gelu": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "qb_wavlm_gate": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "qb_attention_relbias": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "qb_axpy": (C.c_int, [_vp, _f32, _i64, _i32, _vp, _vp]),
+    "qb_ssl_compress": (C.c_int, [_vp, _i64, _i64, _i32, _f32, _i32, _vp, _vp]),
+    "qb_pad_wav": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp]),
     "qb_init": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "qb_handle_free": (None, [_vp]),
     "qb_memcpy_d2d": (C.c_int, [_vp, _vp, _i64, _vp]),

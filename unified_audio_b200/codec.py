@@ -182,6 +182,7 @@ class Codec(nn.Module):
         win = sd["encoder.stft.window"].double()
         fwd = torch.cat([torch.cos(ang) * win, -torch.sin(ang) * win], 0)
         W["dft_fwd"] = _planes_from_f64(fwd, True)
+        W["stft2"] = _stft2_weights(n_fft, sd["encoder.stft.window"].float().contiguous(), dev)
         # inverse real DFT (1/N, Hermitian weights c_k, synthesis window folded in), K padded to a multiple of 64
         kin = _pad_to(2 * nf, 64)
         ck = torch.full((nf,), 2.0, dtype=torch.float64, device=dev)
@@ -336,13 +337,28 @@ class Codec(nn.Module):
         M = B * F
         pc, pd = self.policy["conv"], self.policy["dft"]
         wav = wav.float().contiguous()
-        hb = self._planes("enc_hb", (B, F + 1, hop), pd)
-        ops.wav_to_hopblocks(wav, hop, hb)
-        spec_ = self._buf("enc_spec", (M, g["spec_ld"]))
-        ops.gemm(hb, W["dft_fwd"], 2 * nf, a_batch=B, a_rows_per_batch=F + 1, a_ld=hop, m_per_batch=F, taps=2,
-                 out_f32=rowmap(spec_, g["spec_ld"], F, 0))
         feat = self._planes("enc_feat", (B, F + 2, g["feat_ld"]), pc)
-        ops.stft_post(spec_, g["spec_ld"], B, F, nf, feat, g["feat_ld"], F + 2, 1)
+        s2 = W["stft2"]
+        if s2 is not None and os.environ.get("QB_STFT", "fft") == "fft":
+            # two-stage DFT (csrc/elementwise.cu "two-stage STFT"): MMA chains of 4 / 8 instead of 120 -> fp32-FFT-grade spectrum
+            P, Q = s2["P"], s2["Q"]
+            ga = self._planes("enc_sg", (M * Q, 64), True)
+            ops.stft_gather(wav, hop, n_fft, P, Q, s2["window"], ga)
+            Y = self._buf("enc_sy", (M * Q, 2 * P))
+            ops.gemm(ga, s2["wA"], 2 * P, a_batch=1, a_rows_per_batch=M * Q, a_ld=64, m_per_batch=M * Q, out_f32=rowmap(Y, 2 * P, M * Q, 0))
+            Z = self._planes("enc_sz", (M * P, 128), True)
+            ops.stft_twiddle(Y, 2 * P, M, P, Q, s2["tw"], Z)
+            X = self._buf("enc_sx", (M * P, s2["ldX"]))
+            ops.gemm(Z, s2["wB"], s2["nB"], a_batch=1, a_rows_per_batch=M * P, a_ld=128, m_per_batch=M * P,
+                     out_f32=rowmap(X, s2["ldX"], M * P, 0))
+            ops.stft_post2(X, s2["ldX"], B, F, nf, P, feat, g["feat_ld"], F + 2, 1)
+        else:
+            hb = self._planes("enc_hb", (B, F + 1, hop), pd)
+            ops.wav_to_hopblocks(wav, hop, hb)
+            spec_ = self._buf("enc_spec", (M, g["spec_ld"]))
+            ops.gemm(hb, W["dft_fwd"], 2 * nf, a_batch=B, a_rows_per_batch=F + 1, a_ld=hop, m_per_batch=F, taps=2,
+                     out_f32=rowmap(spec_, g["spec_ld"], F, 0))
+            ops.stft_post(spec_, g["spec_ld"], B, F, nf, feat, g["feat_ld"], F + 2, 1)
         if taps is not None:
             taps["enc.feat"] = feat.float()[:, 1:-1, :2 * nf].transpose(1, 2).clone()
         x0 = self._buf("enc_x0", (M, C))
@@ -575,6 +591,43 @@ class GraphedCall:
                     dst.copy_(src, non_blocking=True)
         self.graph.replay()
         return self.outputs
+
+
+def stft2_factors(n_fft: int):
+    """n_fft = P * Q with P <= 64 and Q <= 64 (P as large as possible): 1920 -> (48, 40), 1280 -> (40, 32); None if impossible"""
+    for P in range(64, 0, -1):
+        if n_fft % P == 0 and n_fft // P <= 64:
+            return P, n_fft // P
+    return None
+
+
+def _stft2_weights(n_fft: int, window: torch.Tensor, dev):
+    """DFT matrices of the two-stage STFT in fp64 (exact argument reduction): W_A [2P, 64], W_B [2*K2, 128], twiddle [Q*P, 2]"""
+    pq = stft2_factors(n_fft)
+    if pq is None:
+        return None
+    P, Q = pq
+    nf = n_fft // 2 + 1
+    K2 = (nf - 1) // P + 1
+    two_pi = 2.0 * math.pi
+    k1 = torch.arange(P, dtype=torch.int64)
+    a = torch.arange(P, dtype=torch.int64)
+    angA = two_pi * (torch.outer(k1, a) % P).double() / P
+    wA = torch.zeros(2 * P, 64, dtype=torch.float64)
+    wA[0::2, :P] = torch.cos(angA)
+    wA[1::2, :P] = -torch.sin(angA)
+    k2 = torch.arange(K2, dtype=torch.int64)
+    b = torch.arange(Q, dtype=torch.int64)
+    angB = two_pi * (torch.outer(k2, b) % Q).double() / Q
+    wB = torch.zeros(2 * K2, 128, dtype=torch.float64)
+    wB[0::2, :Q] = torch.cos(angB)
+    wB[0::2, Q:2 * Q] = torch.sin(angB)
+    wB[1::2, :Q] = -torch.sin(angB)
+    wB[1::2, Q:2 * Q] = torch.cos(angB)
+    angT = two_pi * (torch.outer(b, k1) % n_fft).double() / n_fft          # [b, k1]
+    tw = torch.stack([torch.cos(angT), -torch.sin(angT)], -1).float().reshape(Q * P, 2).contiguous()
+    return dict(P=P, Q=Q, wA=_planes_from_f64(wA.to(dev), True), wB=_planes_from_f64(wB.to(dev), True), tw=tw.to(dev), nB=2 * K2,
+                ldX=_pad_to(2 * K2, 4), window=window)
 
 
 def _planes_from_f64(w: torch.Tensor, split: bool) -> Planes:

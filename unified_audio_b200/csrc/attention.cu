@@ -4,6 +4,7 @@
 // keys staged in shared memory and read as warp-wide broadcasts.  Attention is ~0.5 % of the path's
 // FLOPs; the tensor-core version is a later optimisation.
 #include <atomic>
+#include <vector>
 
 #include "common.cuh"
 #include "quark_b200.h"
@@ -16,7 +17,8 @@ constexpr int ATT_THREADS = 128;
 template <int D, int KT>
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_kernel(const float* __restrict__ qkv, int T, int H, const float* __restrict__ rcos,
-                 const float* __restrict__ rsin, float scale, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+                 const float* __restrict__ rsin, float scale, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                 const float* __restrict__ rel_table = nullptr, const float* __restrict__ gate = nullptr) {
   constexpr int HD = D / 2;
   __shared__ __align__(16) float ks[KT][D];
   __shared__ __align__(16) float vs[KT][D];
@@ -44,6 +46,9 @@ attention_kernel(const float* __restrict__ qkv, int T, int H, const float* __res
 #pragma unroll
   for (int d = 0; d < D; ++d) o[d] = 0.f;
   float m = -INFINITY, l = 0.f;
+  // WavLM gated relative position bias (transformers modeling_wavlm.WavLMAttention): score[i, j] += gate[b, h, i] * table[h, j - i]
+  const float gq = (rel_table && active) ? gate[((long long)b * H + h) * T + tq] : 0.f;
+  const float* relrow = rel_table ? rel_table + (long long)h * (2 * T - 1) + (T - 1) - (active ? tq : 0) : nullptr;
 
   for (int k0 = 0; k0 < T; k0 += KT) {
     __syncthreads();
@@ -79,6 +84,7 @@ attention_kernel(const float* __restrict__ qkv, int T, int H, const float* __res
         acc = fmaf(q[4 * d4 + 2], kk.z, acc);
         acc = fmaf(q[4 * d4 + 3], kk.w, acc);
       }
+      if (relrow && k0 + j < T) acc = fmaf(gq, relrow[k0 + j], acc);
       sc[j] = (k0 + j < T) ? acc : -INFINITY;
       tmax = fmaxf(tmax, sc[j]);
     }
@@ -116,8 +122,69 @@ attention_kernel(const float* __restrict__ qkv, int T, int H, const float* __res
   }
 }
 
+// gate[b, h, t] = ga * (gb * const_h - 1) + 2 with (ga, gb) = sigmoid(sum over groups of 4 of Linear(d -> 8)(x[b, t, head h]))
+// (WavLMAttention.forward: gru_rel_pos_linear / gru_rel_pos_const on the layer INPUT)
+__global__ void wavlm_gate_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                  const float* __restrict__ cst, int T, int H, int D, float* __restrict__ gate, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int h = (int)(i % H);
+  const long long bt = i / H;
+  const int t = (int)(bt % T);
+  const long long b = bt / T;
+  const float* xp = x + bt * (long long)(H * D) + h * D;
+  float p[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    float acc = bias[o];
+    for (int d = 0; d < D; ++d) acc = fmaf(xp[d], w[o * D + d], acc);
+    p[o] = acc;
+  }
+  const float ga = 1.f / (1.f + expf(-(p[0] + p[1] + p[2] + p[3])));
+  const float gb = 1.f / (1.f + expf(-(p[4] + p[5] + p[6] + p[7])));
+  gate[(b * H + h) * T + t] = ga * (gb * cst[h] - 1.f) + 2.f;
+}
+
 }  // namespace qb
 using namespace qb;
+
+extern "C" int qb_wavlm_gate(const float* x, int64_t B, int64_t T, int32_t heads, int32_t head_dim, const float* w, const float* bias,
+                             const float* cst, float* gate, void* stream) {
+  QB_REQUIRE(x && w && bias && cst && gate, "wavlm_gate: bad args");
+  const long long total = B * T * heads;
+  wavlm_gate_kernel<<<(unsigned)ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(x, w, bias, cst, (int)T, heads, head_dim, gate, total);
+  g_launches++;
+  QB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int qb_attention_relbias(const float* qkv, int64_t B, int64_t T, int32_t heads, int32_t head_dim, const float* rel_table,
+                                    const float* gate, qb_half* out_hi, qb_half* out_lo, void* stream) {
+  QB_REQUIRE(qkv && rel_table && gate && out_hi && T > 0 && heads > 0, "attention_relbias: bad args");
+  QB_REQUIRE(head_dim == 64, "attention_relbias: head_dim must be 64 (got %d)", head_dim);
+  // no rotary embedding in WavLM: identity tables (cos = 1, sin = 0) kept in a per-process device buffer of T*64 floats
+  static float* ident[2] = {nullptr, nullptr};
+  static int64_t ident_rows = 0;
+  if (ident_rows < T) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing((cudaStream_t)stream, &cs);
+    QB_REQUIRE(cs == cudaStreamCaptureStatusNone, "attention_relbias: first call for this length must happen outside stream capture");
+    const int64_t rows = (T + 1023) / 1024 * 1024;
+    if (ident[0]) { cudaFree(ident[0]); cudaFree(ident[1]); }
+    QB_CHECK_CUDA(cudaMalloc(&ident[0], (size_t)rows * 64 * 4));
+    QB_CHECK_CUDA(cudaMalloc(&ident[1], (size_t)rows * 64 * 4));
+    std::vector<float> ones((size_t)rows * 64, 1.0f);
+    QB_CHECK_CUDA(cudaMemcpy(ident[0], ones.data(), ones.size() * 4, cudaMemcpyHostToDevice));
+    QB_CHECK_CUDA(cudaMemset(ident[1], 0, (size_t)rows * 64 * 4));
+    ident_rows = rows;
+  }
+  dim3 grid((unsigned)ceil_div(T, ATT_THREADS), (unsigned)heads, (unsigned)B);
+  attention_kernel<64, 32><<<grid, ATT_THREADS, 0, (cudaStream_t)stream>>>(qkv, (int)T, heads, ident[0], ident[1], 0.125f, (__half*)out_hi,
+                                                                         (__half*)out_lo, rel_table, gate);
+  g_launches++;
+  QB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int qb_attention_hd(const float* qkv, int64_t B, int64_t T, int32_t heads, int32_t head_dim, const float* rope_cos,
                                const float* rope_sin, qb_half* out_hi, qb_half* out_lo, void* stream) {

@@ -441,6 +441,70 @@ __global__ void dwconv_kernel(const float* __restrict__ x, const float* __restri
   }
 }
 
+
+// ------------------------------------------------------------------ two-stage (Cooley-Tukey) STFT front end
+// The windowed real DFT of a frame as ONE K = n_fft contraction chains n_fft/16 tensor-core MMAs (x3 split terms) into one
+// accumulator; the tensor core truncates at every accumulate, so the bias grows with the chain: measured 7e-6 of the largest
+// magnitude at K = 1920 - 25x the error of an fp32 FFT, enough to move log|S| of a tiny bin by 1e-2 and to flip the sign of
+// a vanishing imaginary part (phase +-1) ten times per 64 clips.  With n_fft = P*Q, s = Q a + b, k = k1 + P k2:
+//   X[k1 + P k2] = sum_b e^{-2 pi i k2 b / Q} * ( e^{-2 pi i k1 b / n_fft} * sum_a xw[Q a + b] e^{-2 pi i k1 a / P} )
+// i.e. a P-point DFT per residue b (GEMM A, K = P <= 64), a twiddle, a Q-point DFT per k1 (GEMM B, K = 2Q <= 128): chains of
+// 4 and 8 MMAs - fp32-FFT-grade accuracy on the same tensor-core GEMM.
+//   gather:  planes A[(clip, f, b), a] = pad(wav)[hop f + Q a + b] * window[Q a + b]          (a < P; cols P..63 zero)
+//   twiddle: planes Z[(clip, f, k1), c*Q + b] = (Y[(clip, f, b), (k1, c)] * e^{-2 pi i k1 b / n_fft})_c,  c = re / im
+//   post:    log(clip(|X|, 1e-5)), angle(X) / pi with X[k] read at row k % P, column pair k / P
+__global__ void stft_gather_kernel(const float* __restrict__ wav, long long T, int hop, int n_fft, int P, int Q, int F,
+                                   const float* __restrict__ win, __half* __restrict__ hi, __half* __restrict__ lo, long long total) {
+  const int pad = (n_fft - hop) / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int a = (int)(i & 63);
+    const long long row = i >> 6;
+    const int b = (int)(row % Q);
+    const long long cf = row / Q;                   // clip * F + f
+    const int f = (int)(cf % F);
+    const long long clip = cf / F;
+    float v = 0.f;
+    if (a < P) {
+      const int sidx = Q * a + b;
+      const long long src = (long long)hop * f + sidx - pad;
+      if (src >= 0 && src < T) v = wav[clip * T + src] * win[sidx];
+    }
+    store_planes(hi, lo, i, v);
+  }
+}
+__global__ void stft_twiddle_kernel(const float* __restrict__ Y, long long ldY, int P, int Q, const float2* __restrict__ tw,
+                                    __half* __restrict__ hi, __half* __restrict__ lo, long long total) {
+  // one thread per (clip-frame, k1, b): reads the complex Y, writes re at column b and im at column Q + b of row (cf, k1)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i % Q);
+    const int k1 = (int)((i / Q) % P);
+    const long long cf = i / ((long long)Q * P);
+    const float* y = Y + (cf * Q + b) * ldY + 2 * k1;
+    const float yr = y[0], yi = y[1];
+    const float2 w = tw[b * P + k1];                // (cos, -sin)(2 pi k1 b / n_fft)
+    const float zr = fmaf(yr, w.x, -yi * w.y), zi = fmaf(yr, w.y, yi * w.x);
+    const long long o = (cf * P + k1) * 128;
+    store_planes(hi, lo, o + b, zr);
+    store_planes(hi, lo, o + Q + b, zi);
+  }
+}
+__global__ void stft_post2_kernel(const float* __restrict__ X, long long ldX, int frames, int nf, int P, __half* __restrict__ hi,
+                                  __half* __restrict__ lo, long long ld, long long rpb, long long off) {
+  const int f = blockIdx.x, b = blockIdx.y;
+  const float* xr = X + ((long long)b * frames + f) * P * ldX;
+  const long long o = ((long long)b * rpb + off + f) * ld;
+  for (int k = threadIdx.x; k < ld; k += blockDim.x) {
+    if (k < nf) {
+      const float* p = xr + (long long)(k % P) * ldX + 2 * (k / P);
+      const float re = p[0], im = (k == 0 || k == nf - 1) ? 0.f : p[1];
+      store_planes(hi, lo, o + k, logf(fmaxf(hypotf(re, im), 1e-5f)));
+      store_planes(hi, lo, o + nf + k, atan2f(im, re) * 0.31830988618379067154f);
+    } else if (k >= 2 * nf) {
+      store_planes(hi, lo, o + k, 0.f);
+    }
+  }
+}
+
 }  // namespace qb
 using namespace qb;
 
@@ -724,5 +788,34 @@ extern "C" int qb_dwconv(const float* x, const float* w, const float* bias, int6
   QB_REQUIRE(x && w && out && k % 2 == 1, "dwconv: bad args");
   dim3 grid((unsigned)T, (unsigned)B);
   dwconv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, (int)T, (int)C, k, out);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_stft_gather(const float* wav, int64_t B, int64_t T, int32_t hop, int32_t n_fft, int32_t P, int32_t Q,
+                              const float* window, qb_half* hi, qb_half* lo, void* stream) {
+  QB_REQUIRE(wav && window && hi && P * Q == n_fft && P <= 64 && 2 * Q <= 128 && T % hop == 0 && (n_fft - hop) % 2 == 0,
+             "stft_gather: needs n_fft == P*Q, P <= 64, Q <= 64, T a multiple of hop");
+  const int64_t F = T / hop;
+  const long long total = B * F * Q * 64;
+  stft_gather_kernel<<<(unsigned)(ceil_div(total, 256) < 148 * 32 ? ceil_div(total, 256) : 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+      wav, T, hop, n_fft, P, Q, (int)F, window, (__half*)hi, (__half*)lo, total);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_stft_twiddle(const float* Y, int64_t ldY, int64_t frames_total, int32_t P, int32_t Q, const float* twiddle,
+                               qb_half* hi, qb_half* lo, void* stream) {
+  QB_REQUIRE(Y && twiddle && hi && ldY >= 2 * P && 2 * Q <= 128, "stft_twiddle: bad args");
+  const long long total = frames_total * P * Q;
+  stft_twiddle_kernel<<<(unsigned)(ceil_div(total, 256) < 148 * 32 ? ceil_div(total, 256) : 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+      Y, ldY, P, Q, (const float2*)twiddle, (__half*)hi, (__half*)lo, total);
+  QB_LAUNCH_END();
+}
+
+extern "C" int qb_stft_post2(const float* X, int64_t ldX, int64_t B, int64_t frames, int32_t nf, int32_t P, qb_half* hi, qb_half* lo,
+                             int64_t ld, int64_t rows_per_batch, int64_t row_off, void* stream) {
+  QB_REQUIRE(X && hi && 2 * nf <= ld && row_off + frames <= rows_per_batch && ldX >= 2 * ((nf - 1) / P + 1), "stft_post2: bad args");
+  dim3 grid((unsigned)frames, (unsigned)B);
+  stft_post2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldX, (int)frames, nf, P, (__half*)hi, (__half*)lo, ld, rows_per_batch,
+                                                           row_off);
   QB_LAUNCH_END();
 }

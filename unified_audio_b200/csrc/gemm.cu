@@ -45,7 +45,8 @@ struct RowMapD {
 };
 struct GemmParams {
   int tiles_per_batch, num_n_tiles, num_tiles, num_kb;
-  int taps, stride, cblocks, C, dil;
+  int taps, stride, cblocks, C, dil;   // C = channels contracted per tap
+  int Cld;                             // channels per row of the A buffer (row stride); == C unless a_cols is given
   int m_per_batch, N;
   const float* bias;
   const float* gamma;
@@ -302,7 +303,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* s = smem + stage * STAGE_BYTES;
           const int tt = tap * p.dil;      // input row of output row m: m * stride + tap * dilation
-          const int ax = (tt % p.stride) * p.C + cb * BK, ay = m0 + tt / p.stride, wx = tap * p.C + cb * BK;
+          const int ax = (tt % p.stride) * p.Cld + cb * BK, ay = m0 + tt / p.stride, wx = tap * p.C + cb * BK;
           tma_load_3d(s, &tmA_hi, &full[stage], ax, ay, b);
           if (NPL == 2) tma_load_3d(s + A_BYTES, &tmA_lo, &full[stage], ax, ay, b);
           tma_load_2d(s + NPL * A_BYTES, &tmW_hi, &full[stage], wx, n0);
@@ -434,7 +435,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           const uint32_t fb = mapa_u32(smem_u32(&full[stage]), 0);
           uint8_t* s = smem + stage * STAGE_BYTES;
           const int tt = tap * p.dil;      // input row of output row m: m * stride + tap * dilation
-          const int ax = (tt % p.stride) * p.C + cb * BK, ay = m0 + tt / p.stride, wx = tap * p.C + cb * BK;
+          const int ax = (tt % p.stride) * p.Cld + cb * BK, ay = m0 + tt / p.stride, wx = tap * p.C + cb * BK;
           tma2_load_3d(s, &tmA_hi, fb, ax, ay, b);
           if (NPL == 2) tma2_load_3d(s + A_BYTES, &tmA_lo, fb, ax, ay, b);
           tma2_load_2d(s + NPL * A_BYTES, &tmW_hi, fb, wx, n0);
@@ -657,8 +658,8 @@ __global__ void gemm_simt_kernel(const GemmParams p) {
     for (int t = 0; t < p.taps; ++t) {
       long long row = (long long)m * p.stride + (long long)t * p.dil;
       if (row >= p.a_rpb) continue;
-      const __half* ah = p.a_hi + ((long long)b * p.a_rpb + row) * p.C;
-      const __half* al = p.a_lo ? p.a_lo + ((long long)b * p.a_rpb + row) * p.C : nullptr;
+      const __half* ah = p.a_hi + ((long long)b * p.a_rpb + row) * p.Cld;
+      const __half* al = p.a_lo ? p.a_lo + ((long long)b * p.a_rpb + row) * p.Cld : nullptr;
       const __half* wh = p.w_hi + (long long)col * K + (long long)t * p.C;
       const __half* wl = p.w_lo ? p.w_lo + (long long)col * K + (long long)t * p.C : nullptr;
       for (int c = 0; c < p.C; ++c) {
@@ -732,7 +733,9 @@ static int fill_params(const qb_gemm_desc* d, GemmParams* p, int BN) {
   p->tiles_per_batch = (int)ceil_div(d->m_per_batch, 128);
   p->num_n_tiles = (int)ceil_div(d->n, BN);
   p->num_tiles = (int)(d->a_batch * p->tiles_per_batch * p->num_n_tiles);
-  p->taps = d->taps; p->stride = d->stride; p->C = (int)d->a_ld; p->cblocks = (int)(d->a_ld / 64);
+  const int64_t ck = d->a_cols > 0 ? d->a_cols : d->a_ld;
+  QB_REQUIRE(ck % 64 == 0 && ck <= d->a_ld, "gemm: a_cols (%lld) must be a multiple of 64 and <= a_ld", (long long)ck);
+  p->taps = d->taps; p->stride = d->stride; p->C = (int)ck; p->Cld = (int)d->a_ld; p->cblocks = (int)(ck / 64);
   p->dil = d->dilation > 0 ? d->dilation : 1;
   p->num_kb = p->taps * p->cblocks;
   p->m_per_batch = (int)d->m_per_batch; p->N = (int)d->n;
@@ -755,8 +758,9 @@ static int launch_tc(const qb_gemm_desc* d, cudaStream_t st, int num_sms) {
   cuuint64_t adims[3] = {s * C, (cuuint64_t)d->a_rows_per_batch / s, (cuuint64_t)d->a_batch};
   cuuint64_t astr[2] = {s * C * 2, (cuuint64_t)d->a_rows_per_batch * C * 2};
   cuuint32_t abox[3] = {64, 128, 1};
-  cuuint64_t wdims[2] = {(cuuint64_t)d->taps * C, (cuuint64_t)d->n};
-  cuuint64_t wstr[1] = {(cuuint64_t)d->taps * C * 2};
+  const cuuint64_t Ck = (cuuint64_t)(d->a_cols > 0 ? d->a_cols : d->a_ld);
+  cuuint64_t wdims[2] = {(cuuint64_t)d->taps * Ck, (cuuint64_t)d->n};
+  cuuint64_t wstr[1] = {(cuuint64_t)d->taps * Ck * 2};
   cuuint32_t wbox[2] = {64, (cuuint32_t)BN};
   if (int e = make_map(&mA_hi, d->a_hi, 3, adims, astr, abox)) return e;
   if (int e = make_map(&mW_hi, d->w_hi, 2, wdims, wstr, wbox)) return e;
@@ -793,8 +797,9 @@ static int launch_tc2(const qb_gemm_desc* d, cudaStream_t st, int num_sms) {
   cuuint64_t adims[3] = {s * C, (cuuint64_t)d->a_rows_per_batch / s, (cuuint64_t)d->a_batch};
   cuuint64_t astr[2] = {s * C * 2, (cuuint64_t)d->a_rows_per_batch * C * 2};
   cuuint32_t abox[3] = {64, 128, 1};
-  cuuint64_t wdims[2] = {(cuuint64_t)d->taps * C, (cuuint64_t)d->n};
-  cuuint64_t wstr[1] = {(cuuint64_t)d->taps * C * 2};
+  const cuuint64_t Ck = (cuuint64_t)(d->a_cols > 0 ? d->a_cols : d->a_ld);
+  cuuint64_t wdims[2] = {(cuuint64_t)d->taps * Ck, (cuuint64_t)d->n};
+  cuuint64_t wstr[1] = {(cuuint64_t)d->taps * Ck * 2};
   cuuint32_t wbox[2] = {64, (cuuint32_t)(BN / 2)};
   if (int e = make_map(&mA_hi, d->a_hi, 3, adims, astr, abox)) return e;
   if (int e = make_map(&mW_hi, d->w_hi, 2, wdims, wstr, wbox)) return e;

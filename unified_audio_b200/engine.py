@@ -106,7 +106,8 @@ class CodecEngine:
             buf = torch.empty(B, rows, Cc, device="cuda")
             # stream-ordered device copy of the engine's buffer (same stream as the kernels that produced it)
             _lib.check(self.lib.qb_memcpy_d2d(buf.data_ptr(), ptr, n * 4, _stream()))
-            taps[name.decode()] = buf.transpose(1, 2)
+            nm = name.decode()
+            taps[nm] = buf if nm == "dec.final_norm" else buf.transpose(1, 2)     # (the reference keeps this one [B, T, C])
         self._tap_cb = TAP_FN(cb)
         _lib.check(self.lib.qb_codec_set_tap(self.h, self._tap_cb, None))
 

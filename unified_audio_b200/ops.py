@@ -53,11 +53,16 @@ def rowmap(t: Optional[torch.Tensor], ld=0, rows_per_batch=0, row_off=0) -> RowM
 def gemm(a: Planes, w: Planes, n: int, *, a_batch: int, a_rows_per_batch: int, a_ld: int, m_per_batch: int,
          taps: int = 1, stride: int = 1, bias=None, gamma=None, residual: Optional[RowMap] = None, act=ACT_NONE,
          act2=ACT_NONE, out_f32: Optional[RowMap] = None, out_planes: Optional[Planes] = None,
-         out_planes_map=(0, 0, 0), simt: bool = False, dilation: int = 1, act_param=None, act2_param=None):
+         out_planes_map=(0, 0, 0), simt: bool = False, dilation: int = 1, act_param=None, act2_param=None, a_cols: int = 0,
+         a_col_off: int = 0):
     """One dense contraction (see qb_gemm_desc).  Split mode iff both a.lo and w.lo are given."""
     split = a.lo is not None and w.lo is not None
     d = GemmDesc()
     d.a_hi, d.a_lo = _p(a.hi), (_p(a.lo) if split else None)
+    if a_col_off:       # grouped convolution: contract channels [a_col_off, a_col_off + a_cols) of every row
+        d.a_hi = C.c_void_p(a.hi.data_ptr() + 2 * a_col_off)
+        d.a_lo = C.c_void_p(a.lo.data_ptr() + 2 * a_col_off) if split else None
+    d.a_cols = a_cols
     d.a_batch, d.a_rows_per_batch, d.a_ld = a_batch, a_rows_per_batch, a_ld
     d.taps, d.stride, d.m_per_batch, d.dilation = taps, stride, m_per_batch, dilation
     d.w_hi, d.w_lo, d.n = _p(w.hi), (_p(w.lo) if split else None), n
@@ -162,6 +167,19 @@ def wav_to_hopblocks(wav, hop, out: Planes):
 def stft_post(spec, ld_spec, B, frames, nf, out: Planes, ld, rows_per_batch, row_off):
     _lib.check(_lib.load().qb_stft_post(_p(spec), ld_spec, B, frames, nf, _p(out.hi), _p(out.lo), ld, rows_per_batch,
                                         row_off, _stream()))
+
+
+def stft_gather(wav, hop, n_fft, P, Q, window, out: Planes):
+    B, T = wav.shape
+    _lib.check(_lib.load().qb_stft_gather(_p(wav), B, T, hop, n_fft, P, Q, _p(window), _p(out.hi), _p(out.lo), _stream()))
+
+
+def stft_twiddle(Y, ldY, frames_total, P, Q, twiddle, out: Planes):
+    _lib.check(_lib.load().qb_stft_twiddle(_p(Y), ldY, frames_total, P, Q, _p(twiddle), _p(out.hi), _p(out.lo), _stream()))
+
+
+def stft_post2(X, ldX, B, frames, nf, P, out: Planes, ld, rows_per_batch, row_off):
+    _lib.check(_lib.load().qb_stft_post2(_p(X), ldX, B, frames, nf, P, _p(out.hi), _p(out.lo), ld, rows_per_batch, row_off, _stream()))
 
 
 def istft_pre(head, ld_in, M, nf, out: Planes, ld):
@@ -290,6 +308,41 @@ def lm_head_sample_tc(x, B, hidden, w_head_p, rng, max_cols, emb, x_next, out_id
     _lib.check(_lib.load().qb_lm_head_sample_tc(_p(x), B, hidden, _p(w_head_p), _p(rng), max_cols, _p(emb), _p(x_next),
                                                 _p(out_ids), out_stride, _p(pos), _p(slot), _p(pv), _p(pi), _p(logits),
                                                 float(temperature), int(top_k), float(top_p), _p(seed), _p(debug), _stream()))
+
+
+def ssl_conv0_gn_gelu(x, w, gn_w, gn_b, eps, k, stride, out: Planes, ld, rows_per_batch, row_off, y_scratch, workspace):
+    B, T_in = x.shape
+    _lib.check(_lib.load().qb_ssl_conv0_gn_gelu(_p(x), B, T_in, _p(w), w.shape[0], k, stride, _p(gn_w), _p(gn_b), float(eps), _p(y_scratch),
+                                                _p(workspace), _p(out.hi), _p(out.lo), ld, rows_per_batch, row_off, _stream()))
+
+
+def ssl_conv0_workspace_bytes(B, T0, Cc):
+    return int(_lib.load().qb_ssl_conv0_workspace_bytes(B, T0, Cc))
+
+
+def wavlm_gate(x, B, T, heads, head_dim, w, bias, cst, gate):
+    _lib.check(_lib.load().qb_wavlm_gate(_p(x), B, T, heads, head_dim, _p(w), _p(bias), _p(cst), _p(gate), _stream()))
+
+
+def attention_relbias(qkv, B, T, heads, head_dim, rel_table, gate, out: Planes):
+    _lib.check(_lib.load().qb_attention_relbias(_p(qkv), B, T, heads, head_dim, _p(rel_table), _p(gate), _p(out.hi), _p(out.lo), _stream()))
+
+
+def axpy(x, scale, out, accumulate=True):
+    _lib.check(_lib.load().qb_axpy(_p(x), float(scale), x.numel(), int(accumulate), _p(out), _stream()))
+
+
+def ssl_compress(x, B, T, Cc, power, channel_first, out):
+    _lib.check(_lib.load().qb_ssl_compress(_p(x), B, T, Cc, float(power), int(channel_first), _p(out), _stream()))
+
+
+def pad_wav(x, left, T_out, wrap=False):
+    """[B, T] fp32 -> [B, T_out]: out[b, i] = x[b, i - left], zero (or wrapped) outside"""
+    x = x.float().contiguous()
+    B, T = x.shape
+    out = torch.empty(B, T_out, device=x.device)
+    _lib.check(_lib.load().qb_pad_wav(_p(x), B, T, left, T_out, int(wrap), _p(out), _stream()))
+    return out
 
 
 def launch_count() -> int:
