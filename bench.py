@@ -443,6 +443,51 @@ def bench_codec_strong(args, ctx, model, cfg, total):
                 note="last chunk of a shard that is not a multiple of the chunk size is computed in full and trimmed" if n_local % chunk else None)
 
 
+def bench_tokenize(args, ctx, model, cfg):
+    """HCodecTokenizer.tokenize-shaped leg (audio_tokenizer.py:68-74): raw 48 kHz waveform -> pad_wav -> Resample + HuBERT-base (mean of
+    13 hidden states, |x|^0.3) -> Codec.encode -> codes, everything on the device."""
+    from unified_audio_b200 import ops
+    from unified_audio_b200.ssl import HCodecTokenizer, HUBERT_BASE, SSLFrontEnd
+    dev = ctx.dev
+    fe = SSLFrontEnd(HUBERT_BASE, in_rate=48000, compress=True).to(dev)
+    g = torch.Generator(device=dev).manual_seed(99)
+    with torch.no_grad():
+        for n, p in fe.named_parameters():
+            if n.endswith("original0"):
+                continue
+            if p.dim() >= 2:
+                p.copy_(torch.randn(p.shape, generator=g, device=dev) * (1.5 / p[0].numel()) ** 0.5)
+            elif "norm" in n and n.endswith("weight"):
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g, device=dev))
+            else:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g, device=dev))
+        v = fe.encoder.pos_conv_embed.conv.parametrizations.weight.original1
+        fe.encoder.pos_conv_embed.conv.parametrizations.weight.original0.copy_(v.pow(2).sum((0, 1), keepdim=True).sqrt() * 0.5)
+    fe._w = None
+    tok = HCodecTokenizer(model, fe, cfg["sampling_rate"], cfg["encoder_config"]["target_frame_rate"])
+    B = args.batch
+    T = int(args.seconds * cfg["sampling_rate"]) - 700               # not a multiple of the hop: pad_wav has work to do
+    wav = 0.1 * torch.randn(B, T, device=dev, generator=g)
+    for _ in range(2):
+        tok.tokenize(wav)
+    ops.launch_count_reset()
+    ms = ctx.timed(lambda: tok.tokenize(wav), 3)
+    launches = ops.launch_count() // 3
+    # SSL front end algorithmic FLOPs per 16 kHz second: conv stack 4.9 G + 50 frames x (12 layers x 14.2 M + pos conv 9.4 M + proj 0.8 M) x 2
+    frames = B * (T + 700) // 960
+    ssl_flops = B * (T + 700) / 48000 * (4.9e9 + 50 * 2 * (12 * 7.08e6 + 4.7e6 + 0.4e6))
+    enc_flops = frames * (896.1e6 + 105.0e6 + 8.4e6)
+    tf = ctx.world * (ssl_flops + enc_flops) / (ms * 1e-3) / 1e12
+    peaks = load_peaks()
+    del tok, fe
+    return dict(metric="hcodec2_tokenize_samples_per_s", value=ctx.world * B * T / (ms * 1e-3), unit=UNIT, ms_per_step=ms, n_gpus=ctx.world,
+                config=dict(workload=f"HCodecTokenizer.tokenize: {B} clips x {T} samples @ 48 kHz -> pad_wav -> Resample + HuBERT-base features -> "
+                                     "Codec.encode (wav in, codes out)", precision_policy=f"codec {args.precision}; SSL front end 3-term split"),
+                gpu_launches=int(launches),
+                roofline=dict(bound="tensor", achieved=tf, peak=peaks["tf_sus"] * ctx.world, unit="TFLOP/s", frac=tf / (peaks["tf_sus"] * ctx.world),
+                              kernel="whole tokenize path, algorithmic FLOPs (SSL conv stack + 12 encoder layers + codec encoder / semantic encoder / RVQ)"))
+
+
 def run_codec(args, cfg, ctx, collect_secondary):
     from unified_audio_b200 import ops
     from unified_audio_b200.parallel import gather_tokens
@@ -616,6 +661,11 @@ def run_codec(args, cfg, ctx, collect_secondary):
             sec["codec_b256_strong"] = bench_codec_strong(args, ctx, model, cfg, 256)
         except Exception as e:
             sec["codec_b256_strong"] = dict(error=repr(e))
+        try:
+            sec["tokenize_wav_to_codes"] = bench_tokenize(args, ctx, model, cfg)
+        except Exception as e:
+            sec["tokenize_wav_to_codes"] = dict(error=repr(e))
+            torch.cuda.synchronize()
         if world == 1 and args.precision != "accurate":
             try:        # fp32-grade policy (every GEMM a 3-term split) beside the default
                 del graphed

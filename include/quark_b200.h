@@ -284,6 +284,11 @@ int qb_lm_head_argmax_tc(const float* x, int64_t B, int32_t hidden, const qb_hal
                          int32_t max_cols, const float* embedding, float* x_next, int64_t* out_ids, int32_t out_stride,
                          int32_t* pos, int32_t* slot, float* part_val, int32_t* part_idx, void* stream);
 
+/* Teacher-forced loss + accuracy (CustomLlamaModel.loss_function, QuarkAudio-UniSE/model/llm/llm.py:87-104): label-smoothed KL
+ * (reduction batchmean) of log_softmax(logits [M, ld >= V]) against the smoothed one-hot targets [M] int64, and the arg-max
+ * accuracy -> out = {loss, accuracy}; workspace: 2*M floats.  One pass over the logits, deterministic reduction. */
+int qb_lm_loss(const float* logits, int64_t ld, int64_t M, int32_t V, const int64_t* targets, float label_smoothing, float* workspace,
+               float* out, void* stream);
 /* Sampled decoding step (CustomLlamaModel.sample_logits, QuarkAudio-UniSE/model/llm/llm.py:253-289, as called from
  * llm_sft.py:155-161,184-190 with the reference defaults temperature 0.8, top_k 50, top_p 0.95, do_sample=True):
  * as qb_lm_head_argmax_tc, but the head also writes the range logits to `logits` [B][max_cols] and the token is drawn as

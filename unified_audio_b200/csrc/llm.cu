@@ -540,6 +540,73 @@ __global__ void lm_argmax_embed_kernel(const float* __restrict__ part_val, const
 }
 
 
+// ------------------------------------------------------------------------------------------ teacher-forced loss + accuracy
+// CustomLlamaModel.loss_function (QuarkAudio-UniSE/model/llm/llm.py:87-104): label-smoothed KL (batchmean) between
+// log_softmax(logits) and the smoothed one-hot target, plus arg-max accuracy.  One pass over the logits: per row the
+// log-sum-exp, the target logit, the plain sum and the arg-max; with t = 1 - ls on the target and u = ls / (V - 1) elsewhere
+//   KL_row = t log t + ls log u - t logp_target - u (sum_c logit_c - logit_target - (V - 1) lse)
+// A second single-block kernel sums the rows in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+lm_loss_rows_kernel(const float* __restrict__ logits, long long ld, int V, const int64_t* __restrict__ targets, float ls,
+                    float* __restrict__ row_loss, int* __restrict__ row_hit) {
+  const long long row = blockIdx.x;
+  const float* x = logits + row * ld;
+  float m = -INFINITY, sum = 0.f;
+  int am = 0;
+  for (int c = threadIdx.x; c < V; c += 256) {
+    const float v = x[c];
+    sum += v;
+    if (v > m) { m = v; am = c; }
+  }
+  __shared__ float sm[256], ss[256];
+  __shared__ int si[256];
+  sm[threadIdx.x] = m; ss[threadIdx.x] = sum; si[threadIdx.x] = am;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const float mo = sm[threadIdx.x + o];
+      const int io = si[threadIdx.x + o];
+      if (mo > sm[threadIdx.x] || (mo == sm[threadIdx.x] && io < si[threadIdx.x])) { sm[threadIdx.x] = mo; si[threadIdx.x] = io; }
+      ss[threadIdx.x] += ss[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  const float M = sm[0];
+  float e = 0.f;
+  for (int c = threadIdx.x; c < V; c += 256) e += expf(x[c] - M);
+  __shared__ float se[256];
+  se[threadIdx.x] = e;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) se[threadIdx.x] += se[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float lse = M + logf(se[0]);
+    const int tg = (int)targets[row];
+    const float lt = x[tg];
+    const float t = 1.f - ls, u = ls / (float)(V - 1);
+    const float ent = (t > 0.f ? t * logf(t) : 0.f) + (ls > 0.f ? ls * logf(u) : 0.f);
+    row_loss[row] = ent - t * (lt - lse) - u * ((ss[0] - lt) - (float)(V - 1) * lse);
+    row_hit[row] = si[0] == tg;
+  }
+}
+__global__ void lm_loss_reduce_kernel(const float* __restrict__ row_loss, const int* __restrict__ row_hit, long long M,
+                                      float* __restrict__ out) {
+  __shared__ double sl[256];
+  __shared__ long long sh[256];
+  double l = 0.0;
+  long long h = 0;
+  for (long long i = threadIdx.x; i < M; i += 256) { l += row_loss[i]; h += row_hit[i]; }
+  sl[threadIdx.x] = l; sh[threadIdx.x] = h;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sl[threadIdx.x] += sl[threadIdx.x + o]; sh[threadIdx.x] += sh[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = (float)(sl[0] / (double)M); out[1] = (float)((double)sh[0] / (double)M); }
+}
+
 // ------------------------------------------------------------------------------------------ sampled decoding
 // CustomLlamaModel.sample_logits (QuarkAudio-UniSE/model/llm/llm.py:253-289) for one row per CTA, on the range-restricted
 // logits the head kernel wrote: top-k (threshold = k-th largest value, ties kept: `logits < topk[-1]` is what is removed)
@@ -1188,5 +1255,18 @@ extern "C" int qb_lm_head_sample_tc(const float* x, int64_t B, int32_t hidden, c
   QB_CHECK_CUDA(launch_pdl(lm_sample_embed_kernel, dim3((unsigned)B), dim3(256), smem, st, (const float*)logits, (int)max_cols,
                            (const int*)range, (int)B, 1.0f / temperature, (int)top_k, top_p, (const unsigned*)seed, embedding,
                            (int)hidden, x_next, out_ids, (int)out_stride, (int*)pos, (int*)slot, debug));
+  return 0;
+}
+
+extern "C" int qb_lm_loss(const float* logits, int64_t ld, int64_t M, int32_t V, const int64_t* targets, float label_smoothing,
+                          float* workspace /* [2*M] */, float* out /* {loss, accuracy} */, void* stream) {
+  QB_REQUIRE(logits && targets && workspace && out && M >= 1 && V >= 2 && ld >= V, "lm_loss: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* row_loss = workspace;
+  int* row_hit = (int*)(workspace + M);
+  lm_loss_rows_kernel<<<(unsigned)M, 256, 0, st>>>(logits, ld, V, targets, label_smoothing, row_loss, row_hit);
+  lm_loss_reduce_kernel<<<1, 256, 0, st>>>(row_loss, row_hit, M, out);
+  g_launches += 2;
+  QB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -304,13 +304,11 @@ class LLM_SFT(nn.Module):
         logits = torch.empty(M, vpad, device=hs.device)
         ops.gemm(hp, W["head"], V, a_batch=1, a_rows_per_batch=M, a_ld=self.hidden, m_per_batch=M,
                  out_f32=rowmap(logits, vpad, M, 0))
-        logits = logits[:, :V].reshape(B, Lt, V)
-        # label-smoothed KL + accuracy (llm.py:87-104): metric glue on the produced logits
-        flat, tgt = logits.reshape(-1, V), target_ids.reshape(-1)
-        true = torch.full_like(flat, self.label_smoothing / (V - 1))
-        true.scatter_(1, tgt[:, None], 1.0 - self.label_smoothing)
-        loss = torch.nn.functional.kl_div(torch.log_softmax(flat, -1), true, reduction="batchmean")
-        acc = (logits.argmax(-1) == target_ids).float().mean()
+        # label-smoothed KL + accuracy (llm.py:87-104) in one pass over the produced logits (csrc/llm.cu lm_loss_*)
+        la = ops.lm_loss(logits, vpad, M, V, target_ids.reshape(-1).contiguous(), self.label_smoothing)
+        loss, acc = la[0], la[1]
+        if return_logits:
+            logits = logits[:, :V].reshape(B, Lt, V)
         return (loss, acc, logits) if return_logits else (loss, acc)
 
     # ------------------------------------------------------------------ generate (llm_sft.py:93-195)

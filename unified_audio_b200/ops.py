@@ -345,6 +345,14 @@ def pad_wav(x, left, T_out, wrap=False):
     return out
 
 
+def lm_loss(logits, ld, M, V, targets, label_smoothing):
+    """-> float32 [2] = {label-smoothed KL (batchmean), arg-max accuracy}"""
+    ws = torch.empty(2 * M, device=logits.device)
+    out = torch.empty(2, device=logits.device)
+    _lib.check(_lib.load().qb_lm_loss(_p(logits), ld, M, V, _p(targets), float(label_smoothing), _p(ws), _p(out), _stream()))
+    return out
+
+
 def launch_count() -> int:
     return int(_lib.load().qb_launch_count())
 
