@@ -132,6 +132,7 @@ class CodecH1(Codec):
         self.dec_cfg = dict(dim=c["dec_dim"], intermediate_dim=c["dec_inter"])
         self.policy = dict(PRECISION_POLICIES[precision])
         self._w, self._ws = None, {}
+        self.precision, self.engine_mode, self._engine = precision, "python", None     # H-Codec-1.0 is orchestrated from this file
         self.eval()
 
     # ------------------------------------------------------------------ weight repack
