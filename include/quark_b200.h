@@ -284,6 +284,20 @@ int qb_lm_head_argmax_tc(const float* x, int64_t B, int32_t hidden, const qb_hal
                          int32_t max_cols, const float* embedding, float* x_next, int64_t* out_ids, int32_t out_stride,
                          int32_t* pos, int32_t* slot, float* part_val, int32_t* part_idx, void* stream);
 
+/* n_steps cached greedy decode steps in ONE persistent cooperative kernel (csrc/llm_step.cu): the 62 stages of a step (5 per
+ * layer + head + arg-max) are separated by a device-side grid barrier instead of a kernel boundary, weights of the next tile are
+ * requested before the barrier, position / output slot live in registers.  Tile arithmetic identical to
+ * qb_lm_decode_layer_tc / qb_lm_head_argmax_tc (tokens bit-identical).  wqkv..wdown, k_cache, v_cache: HOST arrays of `layers`
+ * device pointers (packed weights as qb_lm_pack_weight writes them, RMSNorm weights folded); x [B, hidden] = embedding of the
+ * first input token on entry / of the last produced token on exit; *pos, *slot (device ints) advance by n_steps; `barrier`: one
+ * device uint32 (zeroed by the call).  B <= 32; shipped LM dimensions only (hidden 512, FFN 2048).
+ * Replaces the decoding loops of llm_sft.py:137-164 / 166-193 (do_sample=False). */
+int qb_lm_decode_steps(float* x, int64_t B, int32_t hidden, int32_t heads, int32_t inter, int32_t layers, const qb_half* const* wqkv,
+                       const qb_half* const* wo, const qb_half* const* wgate, const qb_half* const* wup, const qb_half* const* wdown,
+                       float* const* k_cache, float* const* v_cache, int32_t Lmax, const qb_half* w_head, const int32_t* range,
+                       int32_t max_cols, const float* embedding, const float* rope_cos, const float* rope_sin, float* q_buf,
+                       float* attn_buf, float* mlp_buf, float* part_val, int32_t* part_idx, int64_t* out_ids, int32_t out_stride,
+                       int32_t* pos, int32_t* slot, int32_t n_steps, uint32_t* barrier, void* stream);
 /* Teacher-forced loss + accuracy (CustomLlamaModel.loss_function, QuarkAudio-UniSE/model/llm/llm.py:87-104): label-smoothed KL
  * (reduction batchmean) of log_softmax(logits [M, ld >= V]) against the smoothed one-hot targets [M] int64, and the arg-max
  * accuracy -> out = {loss, accuracy}; workspace: 2*M floats.  One pass over the logits, deterministic reduction. */

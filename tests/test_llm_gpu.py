@@ -207,3 +207,26 @@ def test_lm_rope_table_grows_and_nan_safe(lib):
     gg, ss = m.generate("se", None, None, mix.cuda(), mix.cuda(), do_sample=False)
     torch.cuda.synchronize()                                                     # no illegal address; ids inside the range
     assert int(gg.min()) >= 0 and int(gg.max()) < 64 and int(ss.min()) >= 0 and int(ss.max()) < 128
+
+
+@pytest.mark.parametrize("B,task", [(5, "se"), (32, "se"), (16, "tse")])
+def test_lm_persistent_decode_matches_per_kernel_path(lib, B, task):
+    """csrc/llm_step.cu: the whole greedy decoding loop in one cooperative kernel (device-side grid barriers between the 62 stages
+    of a step) produces bit-identical tokens to the per-kernel path (same tile arithmetic), for both phases (global / semantic)."""
+    from oracle import llama
+    cfg = llama.LM_FULL
+    m, sd = build(cfg, 7, 2.0)
+    g = torch.Generator().manual_seed(40 + B)
+    T = 20
+    mix = torch.randn(B, T, 768, generator=g).cuda()
+    enr = torch.randn(B, 17, 768, generator=g).cuda() if task == "tse" else None
+    outs = {}
+    for kern in ("tc", "persistent", "persistent"):
+        m.decode_kernel = kern
+        gg, ss = m.generate(task, enr, enr, mix, mix, do_sample=False)
+        torch.cuda.synchronize()
+        outs.setdefault(kern, []).append((gg.cpu(), ss.cpu()))
+    (g0, s0), = outs["tc"]
+    for g1, s1 in outs["persistent"]:
+        assert torch.equal(g0, g1) and torch.equal(s0, s1), "persistent decode differs from the per-kernel path"
+    assert g0.shape == (B, 32) and s0.shape == (B, T)

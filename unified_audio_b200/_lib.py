@@ -130,6 +130,8 @@ SIGNATURES = {
     "qb_lm_prefill": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "qb_lm_decode_greedy": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "qb_lm_forward_logits": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "qb_lm_decode_steps": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp,
+                                     _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp]),
     "qb_lm_loss": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _f32, _vp, _vp, _vp]),
     "qb_lm_head_sample_tc": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _i32,
                                        _f32, _vp, _vp, _vp]),

@@ -101,7 +101,9 @@ class LLM_SFT(nn.Module):
         for name, child in tree.named_children():
             self.add_module(name, child)
         self._w, self._ws = None, {}
-        # "tc": packed fp16-split weights + mma.sync + programmatic dependent launch (product);  "simt": fp32 cross-check
+        # "persistent": the whole decoding loop in one cooperative kernel (csrc/llm_step.cu; greedy, shipped dimensions);
+        # "tc": one kernel per stage, packed fp16-split weights + mma.sync + programmatic dependent launch, 8 steps per CUDA graph
+        # (also the sampled-decoding path);  "simt": fp32 cross-check
         self.decode_kernel = os.environ.get("QB_LM_DECODE", "tc")
         self.graph_steps = int(os.environ.get("QB_LM_GRAPH_STEPS", "8"))     # decode steps per replayed CUDA graph
         self._gen_state = {}
@@ -399,7 +401,7 @@ class LLM_SFT(nn.Module):
         # All decode state is on the device, so a graph may hold any number of consecutive steps: one single-step graph
         # plus one of `graph_steps` steps (fewer replays per generation).
         K = max(1, int(self.graph_steps))
-        if use_graph and not st["captured"]:
+        if use_graph and not st["captured"] and not (self.decode_kernel == "persistent" and sampling is None):
             # warm-up outside capture (one-time cudaFuncSetAttribute calls), then restore the mutated state
             xs.copy_(W["emb"][self.global_sos_token_id][None].expand(B, H))
             step()
@@ -416,8 +418,23 @@ class LLM_SFT(nn.Module):
             cache.pos.fill_(cache.length)
             slot.zero_()
         g1, gk = (st["g1"], st["gk"]) if use_graph else (None, None)
+        persistent = (self.decode_kernel == "persistent" and sampling is None and H == 512 and self.n_layers <= 16 and max_cols % 16 == 0)
+        if persistent and "ptrs" not in st:
+            Ls = W["layers"]
+            st["ptrs"] = dict(n=self.n_layers, wqkv=ops.ptr_array([l["wqkv_p"] for l in Ls]), wo=ops.ptr_array([l["wo_p"] for l in Ls]),
+                              wg=ops.ptr_array([l["wg_p"] for l in Ls]), wu=ops.ptr_array([l["wu_p"] for l in Ls]),
+                              wd=ops.ptr_array([l["wd_p"] for l in Ls]), k=ops.ptr_array(cache.k), v=ops.ptr_array(cache.v))
+            st["bar"] = torch.zeros(4, dtype=torch.int32, device=dev)
+            st["dbuf"] = (torch.zeros(B, H, device=dev), torch.zeros(B, H, device=dev), torch.zeros(B, 4 * H, device=dev))
+
+        def run_persistent(n):
+            qb, ab, mb = st["dbuf"]
+            ops.lm_decode_steps(xs, B, H, self.heads, 4 * H, st["ptrs"], cache.Lmax, W["head_p"], rng, max_cols, W["emb"], W["cos"], W["sin"],
+                                qb, ab, mb, pv, pi, out_ids, n_steps, cache.pos, slot, n, st["bar"])
 
         def run(n):
+            if persistent:
+                return run_persistent(n)
             while n > 0:
                 if gk is not None and n >= K:
                     gk.replay()

@@ -345,6 +345,21 @@ def pad_wav(x, left, T_out, wrap=False):
     return out
 
 
+def ptr_array(tensors):
+    """host array of device pointers (kept alive by the caller)"""
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def lm_decode_steps(x, B, hidden, heads, inter, layer_ptrs, Lmax, w_head_p, rng, max_cols, emb, cos, sin, q_buf, attn_buf, mlp_buf, pv, pi,
+                    out_ids, out_stride, pos, slot, n_steps, barrier):
+    """layer_ptrs: dict of ctypes pointer arrays wqkv / wo / wg / wu / wd / k / v (ptr_array)"""
+    L = layer_ptrs
+    _lib.check(_lib.load().qb_lm_decode_steps(_p(x), B, hidden, heads, inter, L["n"], L["wqkv"], L["wo"], L["wg"], L["wu"], L["wd"], L["k"], L["v"],
+                                              Lmax, _p(w_head_p), _p(rng), max_cols, _p(emb), _p(cos), _p(sin), _p(q_buf), _p(attn_buf),
+                                              _p(mlp_buf), _p(pv), _p(pi), _p(out_ids), out_stride, _p(pos), _p(slot), n_steps, _p(barrier),
+                                              _stream()))
+
+
 def lm_loss(logits, ld, M, V, targets, label_smoothing):
     """-> float32 [2] = {label-smoothed KL (batchmean), arg-max accuracy}"""
     ws = torch.empty(2 * M, device=logits.device)
