@@ -661,6 +661,23 @@ def run_codec(args, cfg, ctx, collect_secondary):
             sec["codec_b256_strong"] = bench_codec_strong(args, ctx, model, cfg, 256)
         except Exception as e:
             sec["codec_b256_strong"] = dict(error=repr(e))
+        try:    # SURVEY 8(d) "24 kHz sample-count" reporting shape: 240 000 samples -> pad_wav -> 241 920 (63 tokens, 252 frames)
+            from unified_audio_b200.ssl import pad_wav
+            g24 = torch.Generator().manual_seed(2400 + rank)
+            w24 = pad_wav((0.1 * torch.randn(B, 240000, generator=g24)).to(dev), 3840)
+            f24 = torch.randn(B, 768, w24.shape[1] // 960, generator=g24)
+            f24 = (torch.sign(f24) * f24.abs() ** 0.3).to(dev)
+            g24c = model.graphed("roundtrip", w24, f24)
+            g24c()
+            ms24 = ctx.timed(lambda: g24c(), 3)
+            sec["codec_240k_samples_shape"] = dict(metric=METRIC, value=world * B * 240000 / (ms24 * 1e-3), unit=UNIT, ms_per_step=ms24,
+                                                   config=dict(workload=f"HCodec-2.0 batch={B} x 240 000 samples (padded to {w24.shape[1]}: 63 tokens, "
+                                                                        "252 frames) encode+RVQ+decode", batch_per_gpu=B),
+                                                   path_algorithmic_tflops=world * B * (w24.shape[1] // 960) * FLOP_PER_FRAME / (ms24 * 1e-3) / 1e12)
+            del g24c
+        except Exception as e:
+            sec["codec_240k_samples_shape"] = dict(error=repr(e))
+            torch.cuda.synchronize()
         try:
             sec["tokenize_wav_to_codes"] = bench_tokenize(args, ctx, model, cfg)
         except Exception as e:

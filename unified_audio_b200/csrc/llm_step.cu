@@ -46,6 +46,7 @@ struct StepParams {
   int64_t* out_ids;
   unsigned* bar;
   float eps;
+  int dbg;       // bit 0: skip the grid barriers, bit 1: skip the tile arithmetic (timing aids, QB_LM_STEP_DBG)
 };
 
 enum { TK_QKV = 0, TK_RESID = 1, TK_GATEUP = 2, TK_HEAD = 3 };
@@ -59,21 +60,25 @@ __device__ __forceinline__ void st_mma(float (&d)[4], uint32_t a0, uint32_t a1, 
 __device__ __forceinline__ void worker_sync(int bar_id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// all CTAs of the (cooperative) grid; `epoch` counts arrivals expected so far (thread 0 of every CTA keeps it in a register)
-__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch, unsigned n_ctas) {
+// all CTAs of the (cooperative) grid; `epoch` counts arrivals expected so far (thread 0 of every CTA keeps it in a register).
+// Arrive: one release reduction (cumulative over the CTA's stores ordered before it by the bar.sync); wait: relaxed polls of
+// the one word, then ONE acquire fence (an acquire load per poll costs a fence per iteration).
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch, unsigned n_ctas, int dbg) {
+  if (dbg & 1) { __syncthreads(); return; }      // timing aid only (results undefined)
   __syncthreads();
   if (threadIdx.x == 0) {
     epoch += n_ctas;
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
     unsigned spins = 0;
-    while (ld_acquire_u32(ctr) < epoch) {
+    while (ld_relaxed_u32(ctr) < epoch) {
       if (++spins > (1u << 28)) asm volatile("trap;");
     }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   __syncthreads();
 }
@@ -386,26 +391,26 @@ __global__ void __launch_bounds__(ST_THREADS, 1) lm_decode_steps_kernel(const St
         uint4 wv[2][4];
         int item = w;
         if (item < n_qkv) { QKV::locate(p, L.wqkv, nullptr, H, item, wt, ti); QKV::load_w(ti, H, wt, wv); }
-        grid_barrier(p.bar, epoch, n_ctas);
+        grid_barrier(p.bar, epoch, n_ctas, p.dbg);
         for (; item < n_qkv; item += NWK) {
           if (item != w) { QKV::locate(p, L.wqkv, nullptr, H, item, wt, ti); QKV::load_w(ti, H, wt, wv); }
-          QKV::compute(p, ti, p.x, H, p.q_buf, 0, pos, L.kc, L.vc, item, wt, wv, wsm, wbar);
+          if (!(p.dbg & 2)) QKV::compute(p, ti, p.x, H, p.q_buf, 0, pos, L.kc, L.vc, item, wt, wv, wsm, wbar);
         }
       }
       {  // ---- attention over the cache (keys 0..pos)
-        grid_barrier(p.bar, epoch, n_ctas);
+        grid_barrier(p.bar, epoch, n_ctas, p.dbg);
         for (int item = w; item < n_att; item += NWK)
-          attn_item(p.q_buf, L.kc, L.vc, heads, p.Lmax, pos + 1, p.attn_buf, item % heads, item / heads, wt, wsm, wbar);
+          if (!(p.dbg & 2)) attn_item(p.q_buf, L.kc, L.vc, heads, p.Lmax, pos + 1, p.attn_buf, item % heads, item / heads, wt, wsm, wbar);
       }
       {  // ---- o_proj + residual
         OPJ::Info ti;
         uint4 wv[1][4];
         int item = w;
         if (item < n_o) { OPJ::locate(p, L.wo, nullptr, H, item, wt, ti); OPJ::load_w(ti, H, wt, wv); }
-        grid_barrier(p.bar, epoch, n_ctas);
+        grid_barrier(p.bar, epoch, n_ctas, p.dbg);
         for (; item < n_o; item += NWK) {
           if (item != w) { OPJ::locate(p, L.wo, nullptr, H, item, wt, ti); OPJ::load_w(ti, H, wt, wv); }
-          OPJ::compute(p, ti, p.attn_buf, H, p.x, H, pos, nullptr, nullptr, item, wt, wv, wsm, wbar);
+          if (!(p.dbg & 2)) OPJ::compute(p, ti, p.attn_buf, H, p.x, H, pos, nullptr, nullptr, item, wt, wv, wsm, wbar);
         }
       }
       {  // ---- RMSNorm + gate / up + SwiGLU
@@ -413,10 +418,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) lm_decode_steps_kernel(const St
         uint4 wv[2][4];
         int item = w;
         if (item < n_gu) { GUP::locate(p, L.wg, L.wu, H, item, wt, ti); GUP::load_w(ti, H, wt, wv); }
-        grid_barrier(p.bar, epoch, n_ctas);
+        grid_barrier(p.bar, epoch, n_ctas, p.dbg);
         for (; item < n_gu; item += NWK) {
           if (item != w) { GUP::locate(p, L.wg, L.wu, H, item, wt, ti); GUP::load_w(ti, H, wt, wv); }
-          GUP::compute(p, ti, p.x, H, p.mlp_buf, I, pos, nullptr, nullptr, item, wt, wv, wsm, wbar);
+          if (!(p.dbg & 2)) GUP::compute(p, ti, p.x, H, p.mlp_buf, I, pos, nullptr, nullptr, item, wt, wv, wsm, wbar);
         }
       }
       {  // ---- down + residual: K = inter, the whole CTA (16 warps) per tile
@@ -424,10 +429,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) lm_decode_steps_kernel(const St
         uint4 wv[1][8];
         int item = blockIdx.x;
         if (item < n_o) { DWN::locate(p, L.wd, nullptr, I, item, tid, ti); DWN::load_w(ti, I, tid, wv); }
-        grid_barrier(p.bar, epoch, n_ctas);
+        grid_barrier(p.bar, epoch, n_ctas, p.dbg);
         for (; item < n_o; item += (int)gridDim.x) {
           if (item != (int)blockIdx.x) { DWN::locate(p, L.wd, nullptr, I, item, tid, ti); DWN::load_w(ti, I, tid, wv); }
-          DWN::compute(p, ti, p.mlp_buf, I, p.x, H, pos, nullptr, nullptr, item, tid, wv, smem_all, 0);
+          if (!(p.dbg & 2)) DWN::compute(p, ti, p.mlp_buf, I, p.x, H, pos, nullptr, nullptr, item, tid, wv, smem_all, 0);
         }
       }
     }
@@ -437,16 +442,16 @@ __global__ void __launch_bounds__(ST_THREADS, 1) lm_decode_steps_kernel(const St
       uint4 wv[2][4];
       int item = w;
       if (item < n_head) { HED::locate(p, p.whead, nullptr, H, item, wt, ti); HED::load_w(ti, H, wt, wv); }
-      grid_barrier(p.bar, epoch, n_ctas);
+      grid_barrier(p.bar, epoch, n_ctas, p.dbg);
       for (; item < n_head; item += NWK) {
         if (item != w) { HED::locate(p, p.whead, nullptr, H, item, wt, ti); HED::load_w(ti, H, wt, wv); }
-        HED::compute(p, ti, p.x, H, nullptr, 0, pos, nullptr, nullptr, item, wt, wv, wsm, wbar);
+        if (!(p.dbg & 2)) HED::compute(p, ti, p.x, H, nullptr, 0, pos, nullptr, nullptr, item, wt, wv, wsm, wbar);
       }
-      grid_barrier(p.bar, epoch, n_ctas);
-      for (int b = w; b < p.B; b += NWK) argmax_item(p, n_head, b, slot, wt, wsm, wbar);
+      grid_barrier(p.bar, epoch, n_ctas, p.dbg);
+      for (int b = w; b < p.B; b += NWK) if (!(p.dbg & 2)) argmax_item(p, n_head, b, slot, wt, wsm, wbar);
     }
   }
-  grid_barrier(p.bar, epoch, n_ctas);
+  grid_barrier(p.bar, epoch, n_ctas, p.dbg);
   if (blockIdx.x == 0 && tid == 0) { *p.pos = pos0 + p.n_steps; *p.slot = slot0 + p.n_steps; }
 }
 
@@ -485,6 +490,7 @@ extern "C" int qb_lm_decode_steps(float* x, int64_t B, int32_t hidden, int32_t h
   QB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   QB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_decode_steps_kernel, ST_THREADS, 0));
   QB_REQUIRE(per_sm >= 1, "lm_decode_steps: kernel does not fit on an SM");
+  if (const char* e = getenv("QB_LM_STEP_DBG")) p.dbg = atoi(e);
   int grid = sms;
   if (const char* e = getenv("QB_LM_STEP_CTAS")) grid = atoi(e) > 0 && atoi(e) < sms ? atoi(e) : sms;
   QB_CHECK_CUDA(cudaMemsetAsync(barrier, 0, sizeof(uint32_t), st));
