@@ -346,6 +346,26 @@ int qb_ssl_compress(const float* x, int64_t B, int64_t T, int32_t C, float power
  * F.pad(wavs, (160, 160)) (:51), wrap padding of UniSE segments (QuarkAudio-UniSE/model/model.py:175-181). */
 int qb_pad_wav(const float* x, int64_t B, int64_t T_in, int64_t left, int64_t T_out, int32_t wrap, float* out, void* stream);
 
+/* ---------------------------------------------------------------- H-Codec-1.5 adaptive frame-rate primitives
+ * FlexiCodec._perform_similarity_alignment_vectorized (HCodec-1.5/adaptive/modeling_flexicodec_new.py:828-921): h [B, T, D] fp32 ->
+ * sim [B, T-1] (cosine similarity of consecutive frames), seg [B, T] (frame -> token: a token ends where sim <= threshold or after
+ * max_tokens_per_group frames), lengths [B, T] (frames per token, 0 past the last), n_groups [B].  qb_alignment_matrix expands seg
+ * into the reference's dense [B, G, T] 0/1 matrix for the callers that want it. */
+int qb_similarity_alignment(const float* h, int64_t B, int64_t T, int32_t D, float threshold, int32_t max_tokens_per_group, float* sim,
+                            int32_t* seg, int32_t* lengths, int32_t* n_groups, void* stream);
+int qb_alignment_matrix(const int32_t* seg, int64_t B, int64_t T, int64_t G, float* align, void* stream);
+/* Codec._inject_length_to_codes_index / _extract_length_from_codes_index (HCodec-1.5/vq/codec_adaptive.py:68-80): codes [B, nq, G]
+ * int64, lengths [B, G]: packed = (length - 1) * codebook_size + code; unpack returns code % K and length = code / K + 1 of row 0. */
+int qb_pack_lengths(const int64_t* codes, const int32_t* lengths, int64_t B, int32_t nq, int64_t G, int32_t codebook_size, int64_t* out,
+                    void* stream);
+int qb_unpack_lengths(const int64_t* codes, int64_t B, int32_t nq, int64_t G, int32_t codebook_size, int64_t* plain, int32_t* lengths,
+                      void* stream);
+/* FlexiCodec._deaggregate_features_from_token_lengths (modeling_flexicodec_new.py:1007-1041): x [B, C, G] (4- or 8-byte elements)
+ * repeated per token length -> out [B, C, T_out] zero padded; offsets / totals from qb_length_offsets (exclusive prefix sums). */
+int qb_length_offsets(const int32_t* lengths, int64_t B, int64_t G, int32_t* offsets, int32_t* totals, void* stream);
+int qb_deaggregate(const void* x, int32_t elem_bytes, const int32_t* lengths, const int32_t* offsets, int64_t B, int64_t C, int64_t G,
+                   int64_t T_out, void* out, void* stream);
+
 /* ==========================================================================================================
  * Handle-level contract: what a non-Python caller binds.  A handle owns its repacked weight arena,
  * workspace, KV cache and per-device context; every tensor argument is a caller-owned DEVICE pointer (row-major,

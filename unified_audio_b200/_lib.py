@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libquark_b200.so")
+LIB_PATH = os.environ.get("QB_LIB") or os.path.join(_HERE, "lib", "libquark_b200.so")     # QB_LIB: A/B builds for experiments
 
 ACT_NONE, ACT_GELU, ACT_SWIGLU, ACT_ELU, ACT_TANH, ACT_SNAKE = 0, 1, 2, 3, 4, 5
 
@@ -108,6 +108,12 @@ SIGNATURES = {
     "qb_axpy": (C.c_int, [_vp, _f32, _i64, _i32, _vp, _vp]),
     "qb_ssl_compress": (C.c_int, [_vp, _i64, _i64, _i32, _f32, _i32, _vp, _vp]),
     "qb_pad_wav": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp]),
+    "qb_similarity_alignment": (C.c_int, [_vp, _i64, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "qb_alignment_matrix": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    "qb_pack_lengths": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _i32, _vp, _vp]),
+    "qb_unpack_lengths": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),
+    "qb_length_offsets": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    "qb_deaggregate": (C.c_int, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "qb_init": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "qb_handle_free": (None, [_vp]),
     "qb_memcpy_d2d": (C.c_int, [_vp, _vp, _i64, _vp]),

@@ -114,6 +114,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same wait for warps that have slack (epilogue warps waiting for their accumulator tile, producers waiting for a free stage):
+// try_wait with a suspend-time hint parks the thread in hardware until the phase completes (or the hint expires) instead of
+// spinning on the barrier - the spinning epilogue warps were 16 M issued instructions per GEMM launch (profiles/r02_gemm_issue_
+// analysis.md) on a power-capped part.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 22)) { asm volatile("trap;"); }
+  }
+}
+
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

@@ -39,6 +39,11 @@ static int current_device() {
   return dev >= 0 && dev < QB_MAX_DEVICES ? dev : 0;
 }
 
+// 1: epilogue / producer warps park on their barriers (try_wait with a suspend hint) instead of spinning
+#ifndef QB_PARK
+#define QB_PARK 1
+#endif
+
 struct RowMapD {
   void* ptr;
   long long ld, rpb, off;
@@ -299,7 +304,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int b = m_tile / p.tiles_per_batch, m0 = (m_tile % p.tiles_per_batch) * BM, n0 = n_tile * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-          mbar_wait(&empty[stage], phase ^ 1);
+          if (QB_PARK) mbar_wait_parked(&empty[stage], phase ^ 1); else mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* s = smem + stage * STAGE_BYTES;
           const int tt = tap * p.dil;      // input row of output row m: m * stride + tap * dilation
@@ -351,7 +356,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
       const int b = m_tile / p.tiles_per_batch, m0 = (m_tile % p.tiles_per_batch) * BM, n0 = n_tile * BN;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      mbar_wait(&tfull[acc], acc_phase);
+      if (QB_PARK) mbar_wait_parked(&tfull[acc], acc_phase); else mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + hc * CPW;
 #pragma unroll 1
@@ -430,7 +435,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int n0 = n_tile * BN + rank * (BN / 2);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-          mbar_wait(&empty[stage], phase ^ 1);
+          if (QB_PARK) mbar_wait_parked(&empty[stage], phase ^ 1); else mbar_wait(&empty[stage], phase ^ 1);
           if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
           const uint32_t fb = mapa_u32(smem_u32(&full[stage]), 0);
           uint8_t* s = smem + stage * STAGE_BYTES;
@@ -483,7 +488,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
       const int b = m_tile / p.tiles_per_batch, m0 = (m_tile % p.tiles_per_batch) * 2 * BM + rank * BM, n0 = n_tile * BN;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      mbar_wait(&tfull[acc], acc_phase);
+      if (QB_PARK) mbar_wait_parked(&tfull[acc], acc_phase); else mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + hc * CPW;
 #pragma unroll 1
@@ -566,7 +571,7 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int m0 = (m_super * 2 + (int)pair) * 2 * BM + (int)r * BM;
         const int n0 = n_tile * BN + (int)r * (BN / 2) + (int)pair * (BN / 4);      // this CTA's quarter of the weight tile
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          if (QB_PARK) mbar_wait_parked(&empty[stage], phase ^ 1); else mbar_wait(&empty[stage], phase ^ 1);
           if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
           uint8_t* s = smem + stage * STAGE_BYTES;
           const int kx = kb * BK;
@@ -619,7 +624,7 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const int n_tile = tile % p.num_n_tiles, m_super = tile / p.num_n_tiles;
       const int m0 = (m_super * 2 + (int)pair) * 2 * BM + (int)r * BM, n0 = n_tile * BN;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      mbar_wait(&tfull[acc], acc_phase);
+      if (QB_PARK) mbar_wait_parked(&tfull[acc], acc_phase); else mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + hc * CPW;
 #pragma unroll 1
