@@ -60,7 +60,37 @@ __device__ __forceinline__ float lt_rcp(float x) {
 __device__ __forceinline__ float lt_sigmoid(float x) { return lt_rcp(1.0f + __expf(-x)); }
 __device__ __forceinline__ float lt_tanh(float x) { return fmaf(-2.0f, lt_rcp(1.0f + __expf(2.0f * x)), 1.0f); }
 
-template <int U>
+// ---- A operand from TMEM (round 2).  One step's MMA phase is bound by shared-memory bytes per MMA (profiles/r01_lstm_step_anatomy.md:
+// cycles per MMA ~ (A read + B read + ring fill) / 64 B/clk); an M = 128 A tile reads 128 rows of which 32 are a group's.  With
+// `tcgen05.cp.32x128b.warpx4` the group's 32 rows x 8 halves are copied smem -> TMEM once (512 B, broadcast to the four lane
+// quadrants) and `tcgen05.mma` takes A from TMEM: 1 KB instead of 4 KB of A traffic per MMA.  h is published in the no-swizzle
+// core-matrix layout the copy reads: K-block = [kc = k/8][rb = row/8][row%8][k%8] (8 x 8 halves per core matrix, 128 B).
+// Probe of the instruction semantics: profiles/experiments/ts_mma_probe.cu (2e-6 vs the host on all four quadrants).
+// RESULT (B200, B = 64): bit-identical outputs, but 21.1 us / step against 11.8 us for the shared-memory A operand: the 192
+// `tcgen05.cp` per group-step cost ~100 cycles EACH (first h slot -> last MMA issued: 18.9 k cycles instead of 8.1 k) - the copy's
+// instruction throughput, not its bytes, binds.  Kept behind QB_LSTM_TS=1 as a measured negative result.
+__device__ __forceinline__ uint64_t lt_desc_core(uint32_t addr) {      // 4 core matrices 128 B apart, no swizzle
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(128 >> 4) << 16;
+  d |= (uint64_t)(128 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void lt_cp_32x128b_warpx4(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ void lt_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+constexpr uint32_t LT_TS_ACOL = 256;     // TMEM columns 256..511: two A buffers of LT_KG K-blocks (32 columns each)
+
+template <int U, bool TS>
 __global__ void __launch_bounds__(LT_THREADS, 1)
 lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW,
                const float* __restrict__ xp, int B, int T, int H, __half* __restrict__ out_hi,
@@ -69,7 +99,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW,
   constexpr int HALF = U / 2;                   // units per epilogue thread
   static_assert(N % 16 == 0 && N <= 64 && HALF * 4 % 8 == 0, "unsupported slice width");
   constexpr uint32_t WBLK = N * 128;            // bytes of one [N x 64] K-block of W
-  constexpr uint32_t TCOLS = 4 * N <= 64 ? 64 : (4 * N <= 128 ? 128 : 256);
+  constexpr uint32_t TCOLS = TS ? 512 : (4 * N <= 64 ? 64 : (4 * N <= 128 ? 128 : 256));
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int KB = H / 64;
@@ -147,7 +177,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW,
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(128, N);
       mbar_wait(wbar, 0);
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, phase = 0, abuf = 0;
       for (int t = 1; t < T; ++t) {
         for (int g = 0; g < n_groups; ++g) {
           const uint32_t d_tmem = tmem_base + g * N;
@@ -155,6 +185,24 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW,
             mbar_wait(&full[stage], phase);
             tc_fence_after();
             if (kb0 == 0) ts_first[g] = clock64();
+            if (TS) {
+              // smem -> TMEM: LT_KG K-blocks x 8 chunks of 8 halves, then the MMAs with A in TMEM (in order on this thread's pipe)
+              const uint32_t a_tmem = tmem_base + LT_TS_ACOL + abuf * (LT_KG * 32);
+              const uint32_t slot = smem_u32(ring + stage * LT_SLOT);
+#pragma unroll
+              for (int j = 0; j < LT_KG; ++j)
+#pragma unroll
+                for (int kc = 0; kc < 8; ++kc) lt_cp_32x128b_warpx4(a_tmem + j * 32 + kc * 4, lt_desc_core(slot + j * LT_KBLK + kc * 512));
+#pragma unroll
+              for (int j = 0; j < LT_KG; ++j) {
+                const int kb = kb0 + j;
+                const uint32_t sw = smem_u32(Wsm + (size_t)kb * WBLK);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  lt_umma_ts(d_tmem, a_tmem + j * 32 + k * 8, make_sw128_kmajor_desc(sw + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+              abuf ^= 1;
+            } else
 #pragma unroll
             for (int j = 0; j < LT_KG; ++j) {
               const int kb = kb0 + j;
@@ -234,7 +282,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW,
             const __half2 h2 = __halves2half2(hv[i], hv[i + 1]);
             {
               const int uu = u + i, kbk = uu >> 6, col = uu & 63;
-              const int off = kbk * (int)(LT_KBLK / 2) + lane * 64 + ((((col >> 3) ^ (lane & 7)) << 3) | (col & 7));
+              const int off = TS ? kbk * (int)(LT_KBLK / 2) + ((((col >> 3) * 4 + (lane >> 3)) * 8 + (lane & 7)) << 3 | (col & 7))
+                                 : kbk * (int)(LT_KBLK / 2) + lane * 64 + ((((col >> 3) ^ (lane & 7)) << 3) | (col & 7));
               *reinterpret_cast<__half2*>(hcur + off) = h2;
             }
             *reinterpret_cast<__half2*>(out_hi + o + i) = h2;
@@ -309,7 +358,12 @@ static int lstm_tc_chunk(const float* xp, const qb_half* whh_perm, int U, int B,
   static int poll_ns = -1;
   if (poll_ns < 0) { const char* e = getenv("QB_LSTM_POLL_NS"); poll_ns = e ? atoi(e) : 0; }   // measured 0/16/32/64/128 ns: 11.31 / 11.41 / 11.44 / 11.49 / 11.60 us per step
   void* args[] = {&tmW, &xp, &Bi, &Ti, &Hi, &oh, &ol, &hbuf, &flags, &Bpi, &ng, &poll_ns, &prof};
-  const void* fn = U == 4 ? (const void*)lstm_tc_kernel<4> : U == 8 ? (const void*)lstm_tc_kernel<8> : (const void*)lstm_tc_kernel<12>;
+  static int ts_mode = -1;
+  if (ts_mode < 0) { const char* e = getenv("QB_LSTM_TS"); ts_mode = e ? atoi(e) : 0; }     // 0: A operand from shared memory (product); 1: from TMEM (experiment, see above)
+  const void* fn = ts_mode ? (U == 4 ? (const void*)lstm_tc_kernel<4, true> : U == 8 ? (const void*)lstm_tc_kernel<8, true>
+                                                                                     : (const void*)lstm_tc_kernel<12, true>)
+                           : (U == 4 ? (const void*)lstm_tc_kernel<4, false> : U == 8 ? (const void*)lstm_tc_kernel<8, false>
+                                                                                      : (const void*)lstm_tc_kernel<12, false>);
   QB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   QB_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(LT_THREADS), args, smem, st));
   g_launches++;
