@@ -41,7 +41,7 @@ def param_specs(c):
     nf, dim = c["n_filters"], c["dimension"]
     wn_conv("encoder.model.0.", nf, 1, 7)
     mult, idx = 1, 1
-    for r in RATIOS:
+    for r in c.get("ratios", RATIOS):
         ch = mult * nf
         wn_conv(f"encoder.model.{idx}.block.1.", ch // 2, ch, 3)
         wn_conv(f"encoder.model.{idx}.block.3.", ch, ch // 2, 1)
@@ -124,9 +124,9 @@ def _tf(out, prefix, dim, inter, layers):
         out[p + "post_attention_layernorm.weight"] = ((dim,), "nw")
 
 
-def make_state_dict(c, seed=0):
+def make_state_dict(c, seed=0, specs=None):
     sd = OrderedDict()
-    for name, (shape, kind) in param_specs(c).items():
+    for name, (shape, kind) in (specs or param_specs(c)).items():
         key = name.replace("embed_avg", "embed")
         g = torch.Generator()
         g.manual_seed((seed * 1000003 + zlib.crc32(key.encode())) % (2**63 - 1))
@@ -157,6 +157,12 @@ def make_state_dict(c, seed=0):
         elif kind == "embed":
             layer = int(name.split(".layers.")[1].split(".")[0])
             sd[name] = torch.randn(shape, generator=g) * (0.35 * 0.85 ** layer)
+        elif kind == "ls":            # LayerScale of the H-Codec-1.5 transformers (oracle/hcodec15.py)
+            sd[name] = 0.35 * (1 + 0.2 * torch.randn(shape, generator=g))
+        elif kind == "q":
+            sd[name] = 0.5 * torch.randn(shape, generator=g)
+        else:
+            raise KeyError(kind)
     return sd
 
 
@@ -188,7 +194,7 @@ def seanet_encoder(sd, c, x, taps=None, aten_lstm=True):
     """encoder_modules/seanet.py:121-208 as instantiated at vq/codec.py:30-35.  x [B,1,T] -> [B,dimension,T/640]."""
     h = sconv1d(sd, "encoder.model.0.", x)
     idx = 1
-    for r in RATIOS:
+    for r in c.get("ratios", RATIOS):
         p = f"encoder.model.{idx}."
         y = sconv1d(sd, p + "block.1.", F.elu(h))
         y = sconv1d(sd, p + "block.3.", F.elu(y))
