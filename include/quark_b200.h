@@ -365,6 +365,16 @@ int qb_unpack_lengths(const int64_t* codes, int64_t B, int32_t nq, int64_t G, in
 int qb_length_offsets(const int32_t* lengths, int64_t B, int64_t G, int32_t* offsets, int32_t* totals, void* stream);
 int qb_deaggregate(const void* x, int32_t elem_bytes, const int32_t* lengths, const int32_t* offsets, int64_t B, int64_t C, int64_t G,
                    int64_t T_out, void* out, void* stream);
+/* QueryTokenAggregator (adaptive/model_blocks/mimi/transformer.py:740-826), the data movement either side of its transformer:
+ * qb_agg_interleave builds the [B, T+G, D] sequence (frames in order, the query of a group = group mean + query_embedding right behind
+ * the group's last frame, padded groups = the bare embedding at the tail) from channel-last feats [B, T, D], the frame -> token map
+ * seg [B, T], lengths / offsets [B, G] (contiguous) and n_groups [B]; qpos [B, G] receives the row of every query.
+ * qb_agg_gather reads the transformer's output rows at qpos -> tokens [B*G, D], zero for padded groups. */
+int qb_agg_interleave(const float* feats, const int32_t* seg, const int32_t* lengths, const int32_t* offsets, const int32_t* n_groups,
+                      const float* query_embedding, int64_t B, int64_t T, int64_t G, int32_t D, float* out, int32_t* qpos,
+                      void* stream);
+int qb_agg_gather(const float* x, const int32_t* qpos, const int32_t* n_groups, int64_t B, int64_t L, int64_t G, int32_t D, float* out,
+                  void* stream);
 
 /* ==========================================================================================================
  * Handle-level contract: what a non-Python caller binds.  A handle owns its repacked weight arena,

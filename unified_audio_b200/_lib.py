@@ -114,6 +114,8 @@ SIGNATURES = {
     "qb_unpack_lengths": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),
     "qb_length_offsets": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "qb_deaggregate": (C.c_int, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "qb_agg_interleave": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
+    "qb_agg_gather": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp]),
     "qb_init": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "qb_handle_free": (None, [_vp]),
     "qb_memcpy_d2d": (C.c_int, [_vp, _vp, _i64, _vp]),

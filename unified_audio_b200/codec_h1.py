@@ -57,7 +57,7 @@ def h1_spec(c) -> Dict[str, Dict[str, tuple]]:
     nf, dim = c["n_filters"], c["dimension"]
     wn("model.0.", nf, 1, 7)
     mult, idx = 1, 1
-    for r in RATIOS:
+    for r in c.get("ratios", RATIOS):
         ch = mult * nf
         wn(f"model.{idx}.block.1.", ch // 2, ch, 3)
         wn(f"model.{idx}.block.3.", ch, ch // 2, 1)
@@ -164,7 +164,7 @@ class CodecH1(Codec):
         base = Codec.__new__(Codec)
         stages = []
         idx = 1
-        for r in RATIOS:
+        for r in c.get("ratios", RATIOS):
             stages.append(dict(b1=wn(f"encoder.model.{idx}.block.1."), b3=wn(f"encoder.model.{idx}.block.3."),
                                sc=wn(f"encoder.model.{idx}.shortcut."), down=wn(f"encoder.model.{idx + 2}."), r=r))
             idx += 3

@@ -107,6 +107,48 @@ __global__ void deaggregate_kernel(const T* __restrict__ x, const int* __restric
     for (int r = 0; r < n && o + r < T_out; ++r) dst[r] = v;
   }
 }
+// QueryTokenAggregator input (adaptive/model_blocks/mimi/transformer.py:760-805): the T frames of a clip and one query token per group
+// in one sequence of T + G rows - frame t sits at t + seg[t] (one query has been inserted behind every earlier group), the query of
+// group g right behind the group's last frame (offset + length + g) and holds mean(frames of g) + query_embedding; padded groups
+// (g >= n_groups[b]) fill the tail T + g with the bare embedding.  grid (T + G, B); qpos [B, G] = row of each query.
+__global__ void __launch_bounds__(128)
+agg_interleave_kernel(const float* __restrict__ feats, const int* __restrict__ seg, const int* __restrict__ lengths,
+                      const int* __restrict__ offsets, const int* __restrict__ n_groups, const float* __restrict__ qemb, int T, int G,
+                      int D, float* __restrict__ out, int* __restrict__ qpos) {
+  const int s = blockIdx.x, b = blockIdx.y, L = T + G;
+  const float* fb = feats + (size_t)b * T * D;
+  float* ob = out + (size_t)b * L * D;
+  if (s < T) {
+    const int pos = s + seg[(size_t)b * T + s];
+    for (int d = threadIdx.x; d < D; d += blockDim.x) ob[(size_t)pos * D + d] = fb[(size_t)s * D + d];
+    return;
+  }
+  const int g = s - T;
+  if (g >= n_groups[b]) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) ob[(size_t)(T + g) * D + d] = qemb[d];
+    if (threadIdx.x == 0) qpos[(size_t)b * G + g] = T + g;
+    return;
+  }
+  const int st = offsets[(size_t)b * G + g], len = lengths[(size_t)b * G + g];
+  const int pos = st + len + g;
+  const float inv = 1.f / (float)max(len, 1);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int r = 0; r < len; ++r) acc += fb[(size_t)(st + r) * D + d];
+    ob[(size_t)pos * D + d] = acc * inv + qemb[d];
+  }
+  if (threadIdx.x == 0) qpos[(size_t)b * G + g] = pos;
+}
+// tokens [B*G, D] = rows qpos of x [B, L, D]; zero for padded groups (transformer.py:817-824)
+__global__ void __launch_bounds__(128)
+agg_gather_kernel(const float* __restrict__ x, const int* __restrict__ qpos, const int* __restrict__ n_groups, int L, int G, int D,
+                  float* __restrict__ out) {
+  const int g = blockIdx.x, b = blockIdx.y;
+  const bool live = g < n_groups[b];
+  const float* src = x + ((size_t)b * L + (live ? qpos[(size_t)b * G + g] : 0)) * D;
+  float* dst = out + ((size_t)b * G + g) * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) dst[d] = live ? src[d] : 0.f;
+}
 static inline unsigned ad_grid(long long total) {
   long long g = (total + 255) / 256;
   return (unsigned)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -170,6 +212,26 @@ extern "C" int qb_deaggregate(const void* x, int32_t elem_bytes, const int32_t* 
   else
     deaggregate_kernel<int64_t><<<ad_grid(total), 256, 0, (cudaStream_t)stream>>>((const int64_t*)x, lengths, offsets, (int)C, (int)G,
                                                                                  (int)T_out, (int64_t*)out, total);
+  g_launches++;
+  QB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int qb_agg_interleave(const float* feats, const int32_t* seg, const int32_t* lengths, const int32_t* offsets,
+                                 const int32_t* n_groups, const float* query_embedding, int64_t B, int64_t T, int64_t G, int32_t D,
+                                 float* out, int32_t* qpos, void* stream) {
+  QB_REQUIRE(feats && seg && lengths && offsets && n_groups && query_embedding && out && qpos && B >= 1 && T >= 1 && G >= 1 && D >= 1,
+             "agg_interleave: bad args");
+  agg_interleave_kernel<<<dim3((unsigned)(T + G), (unsigned)B), 128, 0, (cudaStream_t)stream>>>(feats, seg, lengths, offsets, n_groups,
+                                                                                               query_embedding, (int)T, (int)G, D, out, qpos);
+  g_launches++;
+  QB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int qb_agg_gather(const float* x, const int32_t* qpos, const int32_t* n_groups, int64_t B, int64_t L, int64_t G, int32_t D,
+                             float* out, void* stream) {
+  QB_REQUIRE(x && qpos && n_groups && out && B >= 1 && G >= 1 && L >= G && D >= 1, "agg_gather: bad args");
+  agg_gather_kernel<<<dim3((unsigned)G, (unsigned)B), 128, 0, (cudaStream_t)stream>>>(x, qpos, n_groups, (int)L, (int)G, D, out);
   g_launches++;
   QB_CHECK_CUDA(cudaGetLastError());
   return 0;

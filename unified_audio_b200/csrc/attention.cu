@@ -14,37 +14,41 @@ extern std::atomic<long long> g_launches;
 
 constexpr int ATT_THREADS = 128;
 
-template <int D, int KT>
+// PARTS threads share one query row, each owning D / PARTS of the head dims (q, o in registers: D = 128 would not fit one thread);
+// the partial dot products are summed across the PARTS adjacent lanes.
+template <int D, int KT, int PARTS = 1>
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_kernel(const float* __restrict__ qkv, int T, int H, const float* __restrict__ rcos,
                  const float* __restrict__ rsin, float scale, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                  const float* __restrict__ rel_table = nullptr, const float* __restrict__ gate = nullptr) {
-  constexpr int HD = D / 2;
+  constexpr int HD = D / 2, DP = D / PARTS, ROWS = ATT_THREADS / PARTS;
+  static_assert(PARTS == 1 || PARTS == 2 || PARTS == 4, "PARTS lanes must sit in one warp");
   __shared__ __align__(16) float ks[KT][D];
   __shared__ __align__(16) float vs[KT][D];
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int tq = qt * ATT_THREADS + threadIdx.x;
+  const int part = threadIdx.x % PARTS, d0 = part * DP;
+  const int tq = qt * ROWS + threadIdx.x / PARTS;
   const long long pitch = 3LL * H * D;
   const float* base = qkv + (long long)b * T * pitch;
   const bool active = tq < T;
 
-  float q[D], o[D];
+  float q[DP], o[DP];
   if (active) {
     const float* qp = base + (long long)tq * pitch + h * D;
     const float* c = rcos + (long long)tq * D;
     const float* s = rsin + (long long)tq * D;
 #pragma unroll
-    for (int d = 0; d < HD; ++d) {
-      float x1 = qp[d], x2 = qp[d + HD];
-      q[d] = (x1 * c[d] - x2 * s[d]) * scale;             // q*cos + rotate_half(q)*sin, then * head_dim^-0.5
-      q[d + HD] = (x2 * c[d + HD] + x1 * s[d + HD]) * scale;
+    for (int j = 0; j < DP; ++j) {                          // q*cos + rotate_half(q)*sin, then * head_dim^-0.5
+      const int d = d0 + j;
+      const float x = qp[d], y = d < HD ? -qp[d + HD] : qp[d - HD];
+      q[j] = (x * c[d] + y * s[d]) * scale;
     }
   } else {
 #pragma unroll
-    for (int d = 0; d < D; ++d) q[d] = 0.f;
+    for (int j = 0; j < DP; ++j) q[j] = 0.f;
   }
 #pragma unroll
-  for (int d = 0; d < D; ++d) o[d] = 0.f;
+  for (int j = 0; j < DP; ++j) o[j] = 0.f;
   float m = -INFINITY, l = 0.f;
   // WavLM gated relative position bias (transformers modeling_wavlm.WavLMAttention): score[i, j] += gate[b, h, i] * table[h, j - i]
   const float gq = (rel_table && active) ? gate[((long long)b * H + h) * T + tq] : 0.f;
@@ -75,15 +79,17 @@ attention_kernel(const float* __restrict__ qkv, int T, int H, const float* __res
 #pragma unroll
     for (int j = 0; j < KT; ++j) {
       float acc = 0.f;
-      const float4* kr = reinterpret_cast<const float4*>(ks[j]);
+      const float4* kr = reinterpret_cast<const float4*>(ks[j] + d0);
 #pragma unroll
-      for (int d4 = 0; d4 < D / 4; ++d4) {
+      for (int d4 = 0; d4 < DP / 4; ++d4) {
         float4 kk = kr[d4];
         acc = fmaf(q[4 * d4], kk.x, acc);
         acc = fmaf(q[4 * d4 + 1], kk.y, acc);
         acc = fmaf(q[4 * d4 + 2], kk.z, acc);
         acc = fmaf(q[4 * d4 + 3], kk.w, acc);
       }
+      if (PARTS > 1) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (PARTS > 2) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
       if (relrow && k0 + j < T) acc = fmaf(gq, relrow[k0 + j], acc);
       sc[j] = (k0 + j < T) ? acc : -INFINITY;
       tmax = fmaxf(tmax, sc[j]);
@@ -92,14 +98,14 @@ attention_kernel(const float* __restrict__ qkv, int T, int H, const float* __res
     const float corr = expf(m - m_new);   // m = -inf on the first tile -> 0
     l *= corr;
 #pragma unroll
-    for (int d = 0; d < D; ++d) o[d] *= corr;
+    for (int j = 0; j < DP; ++j) o[j] *= corr;
 #pragma unroll
     for (int j = 0; j < KT; ++j) {
       const float pj = expf(sc[j] - m_new);
       l += pj;
-      const float4* vr = reinterpret_cast<const float4*>(vs[j]);
+      const float4* vr = reinterpret_cast<const float4*>(vs[j] + d0);
 #pragma unroll
-      for (int d4 = 0; d4 < D / 4; ++d4) {
+      for (int d4 = 0; d4 < DP / 4; ++d4) {
         float4 vv = vr[d4];
         o[4 * d4] = fmaf(pj, vv.x, o[4 * d4]);
         o[4 * d4 + 1] = fmaf(pj, vv.y, o[4 * d4 + 1]);
@@ -111,13 +117,13 @@ attention_kernel(const float* __restrict__ qkv, int T, int H, const float* __res
   }
   if (active) {
     const float inv = 1.f / l;
-    const long long ob = ((long long)b * T + tq) * (long long)(H * D) + h * D;
+    const long long ob = ((long long)b * T + tq) * (long long)(H * D) + h * D + d0;
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
+    for (int j = 0; j < DP; ++j) {
       __half hh, ll;
-      split_f16(o[d] * inv, hh, ll);
-      out_hi[ob + d] = hh;
-      if (out_lo) out_lo[ob + d] = ll;
+      split_f16(o[j] * inv, hh, ll);
+      out_hi[ob + j] = hh;
+      if (out_lo) out_lo[ob + j] = ll;
     }
   }
 }
@@ -189,10 +195,14 @@ extern "C" int qb_attention_relbias(const float* qkv, int64_t B, int64_t T, int3
 extern "C" int qb_attention_hd(const float* qkv, int64_t B, int64_t T, int32_t heads, int32_t head_dim, const float* rope_cos,
                                const float* rope_sin, qb_half* out_hi, qb_half* out_lo, void* stream) {
   QB_REQUIRE(qkv && rope_cos && rope_sin && out_hi && T > 0 && heads > 0, "attention: bad args");
-  QB_REQUIRE(head_dim == 64 || head_dim == 96, "attention: head_dim must be 64 or 96 (got %d)", head_dim);
+  QB_REQUIRE(head_dim == 64 || head_dim == 96 || head_dim == 128, "attention: head_dim must be 64, 96 or 128 (got %d)", head_dim);
   dim3 grid((unsigned)ceil_div(T, ATT_THREADS), (unsigned)heads, (unsigned)B);
   const float scale = 1.0f / sqrtf((float)head_dim);
-  if (head_dim == 64)
+  if (head_dim == 128) {
+    grid.x = (unsigned)ceil_div(T, ATT_THREADS / 2);
+    attention_kernel<128, 16, 2><<<grid, ATT_THREADS, 0, (cudaStream_t)stream>>>(qkv, (int)T, heads, rope_cos, rope_sin, scale,
+                                                                               (__half*)out_hi, (__half*)out_lo);
+  } else if (head_dim == 64)
     attention_kernel<64, 32><<<grid, ATT_THREADS, 0, (cudaStream_t)stream>>>(qkv, (int)T, heads, rope_cos, rope_sin, scale,
                                                                            (__half*)out_hi, (__half*)out_lo);
   else
