@@ -66,6 +66,10 @@ def random_init_(model, seed: int):
             if "rnn." in name:
                 H = p.shape[-1] if p.dim() == 2 else p.shape[0] // 4
                 p.copy_((torch.rand(p.shape, generator=g, device=dev) * 2 - 1) / H ** 0.5)
+            elif name.endswith("layer_scale_1.scale") or name.endswith("layer_scale_2.scale"):     # H-Codec-1.5 mimi LayerScale
+                p.copy_(0.35 * (1 + 0.2 * torch.randn(p.shape, generator=g, device=dev)))
+            elif name.endswith("weight_g"):
+                p.copy_(1 + 0.2 * torch.rand(p.shape, generator=g, device=dev))
             elif name.endswith("gamma"):
                 n_layers = 24 if name.startswith("encoder.") else 32
                 p.copy_((1.0 / n_layers) * (1 + 0.2 * torch.randn(p.shape, generator=g, device=dev)))
@@ -488,6 +492,74 @@ def bench_tokenize(args, ctx, model, cfg):
                               kernel="whole tokenize path, algorithmic FLOPs (SSL conv stack + 12 encoder layers + codec encoder / semantic encoder / RVQ)"))
 
 
+def bench_h15(args, ctx):
+    """H-Codec-1.5 adaptive frame-rate codec, shipped config (conf/config_adaptive_v3.yaml), `batch` clips x `seconds` s at
+    16 kHz: encode (SEANet + semantic encoder + similarity alignment + 2 x 32-layer query-token aggregators + RVQ + length packing)
+    -> decode (unpack + de-aggregate + 32-layer bottleneck transformer + decoder).  Launched kernel by kernel: the sequence lengths
+    T + G depend on the batch's largest group count (one host read per encode / decode, as in the reference)."""
+    from unified_audio_b200 import ops
+    from unified_audio_b200.codec_h15 import CodecH15, H15
+    dev = ctx.dev
+    model = CodecH15(precision=args.precision if args.precision in ("mixed", "accurate", "mixed_dec16", "fast") else "mixed", _cfg=dict(H15)).to(dev)
+    random_init_(model, 4321)
+    B, T50 = args.batch, int(args.seconds * 50)
+    T50 -= T50 % 2
+    g = torch.Generator(device=dev).manual_seed(1500 + ctx.rank)
+    wav = 0.1 * torch.randn(B, 1, T50 * 320, generator=g, device=dev)
+    # semantic features in runs (mean 7.7 frames) + noise (so that tokens of 1..8 frames occur), compressed like the SSL front end's output
+    ids = torch.cumsum((torch.rand(B, T50, generator=g, device=dev) < 0.13).long(), 1)                     # frame -> run index
+    base = torch.randn(B, T50 + 1, 1024, generator=g, device=dev)
+    f = torch.gather(base, 1, ids[..., None].expand(-1, -1, 1024)).transpose(1, 2) + 0.25 * torch.randn(B, 1024, T50, generator=g, device=dev)
+    feat = (torch.sign(f) * f.abs() ** 0.3).contiguous()
+    del base, f
+
+    def step():
+        out = model.encode(wav, feat)
+        return out, model.decode(out["acoustic_codes"], out["semantic_codes"])
+    # one counted step: GEMM FLOPs as the algorithm states them (2 M N K, one pass) + attention (4 L^2 C per layer and item)
+    flops = [0.0]
+    real_gemm, real_att, real_att_tc = ops.gemm, ops.attention_hd, ops.attention_tc
+
+    def count_gemm(a, w, n, **kw):
+        flops[0] += 2.0 * kw["a_batch"] * kw["m_per_batch"] * n * kw.get("taps", 1) * (kw.get("a_cols") or kw["a_ld"])
+        return real_gemm(a, w, n, **kw)
+
+    def count_att(qkv, B_, T_, heads, hd, *a):
+        flops[0] += 4.0 * B_ * T_ * T_ * heads * hd
+        return real_att(qkv, B_, T_, heads, hd, *a)
+
+    def count_att_tc(qkv, B_, T_, heads, *a):
+        flops[0] += 4.0 * B_ * T_ * T_ * heads * 64
+        return real_att_tc(qkv, B_, T_, heads, *a)
+    ops.gemm, ops.attention_hd, ops.attention_tc = count_gemm, count_att, count_att_tc
+    try:
+        out, rec = step()
+    finally:
+        ops.gemm, ops.attention_hd, ops.attention_tc = real_gemm, real_att, real_att_tc
+    torch.cuda.synchronize()
+    from unified_audio_b200 import adaptive
+    _, lens = adaptive.extract_lengths(out["acoustic_codes"], model.codebook_size)
+    n_tok = (lens > 0).sum(1).float()
+    step()
+    ops.launch_count_reset()
+    ms = ctx.timed(step, max(2, min(args.steps, 3)))
+    launches = ops.launch_count() // max(2, min(args.steps, 3))
+    peaks = load_peaks()
+    tf = ctx.world * flops[0] / (ms * 1e-3) / 1e12
+    n_samples = B * T50 * 320
+    del model
+    torch.cuda.empty_cache()
+    return dict(metric="hcodec15_adaptive_encode_decode_samples_per_s", value=ctx.world * n_samples / (ms * 1e-3), unit=UNIT, ms_per_step=ms,
+                n_gpus=ctx.world, scaling="weak",
+                config=dict(workload=f"HCodec-1.5 adaptive (config_adaptive_v3) batch={B} x {T50 / 50:g} s @16 kHz encode + decode, threshold 0.6",
+                            batch_per_gpu=B, frames_25hz=T50 // 2, tokens_per_clip_mean=float(n_tok.mean()), tokens_per_clip_max=int(n_tok.max()),
+                            precision_policy=args.precision, launch="kernel by kernel (data-dependent sequence lengths)"),
+                gpu_launches=int(launches),
+                roofline=dict(bound="tensor", achieved=tf, peak=peaks["tf_sus"] * ctx.world, unit="TFLOP/s", frac=tf / (peaks["tf_sus"] * ctx.world),
+                              kernel="whole encode + decode, algorithmic FLOPs (every GEMM 2MNK once + attention 4 L^2 C)",
+                              flops_per_step=flops[0]))
+
+
 def run_codec(args, cfg, ctx, collect_secondary):
     from unified_audio_b200 import ops
     from unified_audio_b200.parallel import gather_tokens
@@ -865,7 +937,7 @@ def main():
     ap.add_argument("--precision", default="mixed")
     ap.add_argument("--ref-clips", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="all", choices=["all", "codec", "lm", "lm_tse", "lm_forward", "bicodec"],
+    ap.add_argument("--workload", default="all", choices=["all", "codec", "lm", "lm_tse", "lm_forward", "bicodec", "h15"],
                     help="all (default, the driver's line) = the codec line (BASELINE configs[1]) with the UniSE AR-LM legs (configs[2], [3], "
                          "[4]) under `secondary`; codec / lm / lm_tse / lm_forward / bicodec = that line alone")
     ap.add_argument("--quick", action="store_true", help="profiling aid: W warm-up + K steps only, no e2e/roofline/cpu legs")
@@ -884,6 +956,12 @@ def main():
             return
         return run_reference(args, cfg)
     ctx = Ctx()
+    if args.workload == "h15":
+        out = bench_h15(args, ctx)
+        if ctx.rank == 0:
+            print(json.dumps(out))
+        ctx.close()
+        return
     if args.workload in ("lm", "lm_tse", "lm_forward"):
         m = build_lm(ctx.dev)
         if args.workload == "lm_forward":
@@ -909,7 +987,8 @@ def main():
         for name, fn in (("lm_sr", lambda: bench_lm_generate(args, ctx, m, "se", 32, with_cpu=with_cpu)),
                          ("lm_tse", lambda: bench_lm_generate(args, ctx, m, "tse", 16, with_cpu=with_cpu)),
                          ("lm_sr_b256_strong", lambda: bench_lm_generate(args, ctx, m, "se", None, total_batch=256, steps=2)),
-                         ("lm_forward", lambda: bench_lm_forward(args, ctx, m))):
+                         ("lm_forward", lambda: bench_lm_forward(args, ctx, m)),
+                         ("hcodec15_adaptive", lambda: bench_h15(args, ctx))):
             try:
                 sec[name] = fn()
             except Exception as e:          # a secondary leg never takes the headline line down

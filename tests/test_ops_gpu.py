@@ -184,6 +184,37 @@ def test_attention(lib):
     assert e2 < 3e-3
 
 
+@pytest.mark.parametrize("D,split", [(64, True), (64, False), (128, True), (128, False)])
+@pytest.mark.parametrize("B,T,H", [(2, 37, 3), (1, 64, 2), (3, 250, 8), (2, 382, 4), (1, 515, 2)])
+def test_attention_umma(lib, D, split, B, T, H):
+    """tcgen05 attention (csrc/attention_umma.cu) against fp64 softmax attention; ragged lengths exercise the TMA zero fill of the
+    last query / key tiles, 515 the 9-tile K/V ring; and against the fp32 SIMT kernel it replaces"""
+    from unified_audio_b200 import ops
+    qkv = _mk((B, T, 3 * H * D), 31 + T)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2).float() / D))
+    fr = torch.arange(T).float()[:, None] * inv[None]
+    emb = torch.cat([fr, fr], -1)
+    cos, sin = emb.cos().to(DEV).contiguous(), emb.sin().to(DEV).contiguous()
+    out = ops.Planes.zeros((B, T, H * D), split, DEV)
+    ws = torch.zeros(ops.attention_umma_workspace_bytes(B, T, H, D, split), dtype=torch.uint8, device=DEV)
+    ops.attention_umma(qkv, B, T, H, D, cos, sin, out, ws)
+    torch.cuda.synchronize()
+    q, k, v = [t.reshape(B, T, H, D).transpose(1, 2).double() for t in qkv.chunk(3, -1)]
+    rot = lambda x: torch.cat([-x[..., D // 2:], x[..., :D // 2]], -1)
+    c, s = cos.double(), sin.double()
+    q, k = q * c + rot(q) * s, k * c + rot(k) * s
+    att = torch.softmax(q @ k.transpose(2, 3) * D ** -0.5, -1)
+    ref = (att @ v).transpose(1, 2).reshape(B, T, H * D)
+    got = planes_ref(out) if split else out.hi.double()
+    e = relerr(got, ref)
+    print(f"attention_umma D={D} split={split} B={B} T={T} H={H}: relerr {e:.2e}")
+    assert e < (2e-5 if split else 3e-3)
+    simt = ops.Planes.zeros((B, T, H * D), True, DEV)
+    ops.attention_hd(qkv, B, T, H, D, cos, sin, simt)
+    torch.cuda.synchronize()
+    assert relerr(got, planes_ref(simt)) < (2e-5 if split else 3e-3)
+
+
 @pytest.mark.parametrize("B,T,H", [(2, 9, 256), (3, 20, 512), (5, 12, 1536), (70, 6, 512), (130, 5, 256)])
 def test_lstm(lib, B, T, H):
     from unified_audio_b200 import ops

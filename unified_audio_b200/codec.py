@@ -300,8 +300,11 @@ class Codec(nn.Module):
         ws = self._buf("lstm_ws", (max(ops.lstm_workspace_bytes(B, C), ops.lstm_tc_workspace_bytes(B, C)),), torch.uint8)
         lstm_u = ops.lstm_tc_units(C) if use_tc else 0
         cos, sin = self._rope(F, hd)
-        tc_att = (not pa) and hd == 64
-        att_ws = self._buf("att_ws", (ops.attention_tc_workspace_bytes(B, F, heads),), torch.uint8) if tc_att else None
+        legacy = os.environ.get("QB_ATTENTION", "umma") == "legacy"
+        umma = (not legacy) and hd in (64, 128)          # tcgen05 attention (csrc/attention_umma.cu), both precision policies
+        tc_att = (not umma) and (not pa) and hd == 64
+        att_ws = (self._buf("att5_ws", (ops.attention_umma_workspace_bytes(B, F, heads, hd, pa),), torch.uint8) if umma else
+                  self._buf("att_ws", (ops.attention_tc_workspace_bytes(B, F, heads),), torch.uint8) if tc_att else None)
         xm = rowmap(x, C, M, 0)
         for L in layers:
             ops.rmsnorm(x, L["in_w"], M, C, t_a)
@@ -311,7 +314,9 @@ class Codec(nn.Module):
             else:
                 ops.lstm(xp, L["whh"], B, F, C, t_b, ws)
             self._linear(t_b, L["wqkv"], 3 * C, M, C, bias=L["bqkv"], out_f32=rowmap(qkv, 3 * C, M, 0))
-            if tc_att:   # single-pass fp16 policy, head_dim 64: tensor-core flash attention
+            if umma:
+                ops.attention_umma(qkv, B, F, heads, hd, cos, sin, t_a, att_ws, split=pa)
+            elif tc_att:   # legacy: single-pass fp16 policy, head_dim 64: mma.sync flash attention
                 ops.attention_tc(qkv, B, F, heads, cos, sin, t_a, att_ws)
             else:        # split-precision policy or head_dim 96: fp32 SIMT attention
                 ops.attention_hd(qkv, B, F, heads, hd, cos, sin, t_a)

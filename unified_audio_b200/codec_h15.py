@@ -27,6 +27,7 @@ sizes the T + G sequences; decode reads the largest total length the same way (p
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict
 
 import torch
@@ -160,13 +161,17 @@ class CodecH15(CodecH1):
         hid = self._planes("mm_hid", (M, FF), split)
         qkv = self._buf("mm_qkv", (M, 3 * C))
         cos, sin = self._rope_mimi(L, hd)
-        tc_att = (not split) and hd == 64
-        att_ws = self._buf("att_ws", (ops.attention_tc_workspace_bytes(B, L, heads),), torch.uint8) if tc_att else None
+        umma = hd in (64, 128) and os.environ.get("QB_ATTENTION", "umma") != "legacy"      # tcgen05 attention (csrc/attention_umma.cu)
+        tc_att = (not umma) and (not split) and hd == 64
+        att_ws = (self._buf("att5_ws", (ops.attention_umma_workspace_bytes(B, L, heads, hd, split),), torch.uint8) if umma else
+                  self._buf("att_ws", (ops.attention_tc_workspace_bytes(B, L, heads),), torch.uint8) if tc_att else None)
         xm = rowmap(x, C, M, 0)
         for i, Lw in enumerate(layers):
             ops.layernorm(x, Lw["n1w"], Lw["n1b"], 1, M, C, eps=1e-5, out=t_a)
             self._linear(t_a, Lw["wqkv"], 3 * C, M, C, out_f32=rowmap(qkv, 3 * C, M, 0))
-            if tc_att:
+            if umma:
+                ops.attention_umma(qkv, B, L, heads, hd, cos, sin, t_b, att_ws)
+            elif tc_att:
                 ops.attention_tc(qkv, B, L, heads, cos, sin, t_b, att_ws)
             else:
                 ops.attention_hd(qkv, B, L, heads, hd, cos, sin, t_b)

@@ -516,8 +516,12 @@ static int run_transformer(qb_codec* c, const std::vector<TfLayerW>& layers, flo
   QB_TRY(c->ws.f32(&xp, "tf_xp", (size_t)M * 4 * C));
   QB_TRY(c->ws.f32(&qkv, "tf_qkv", (size_t)M * 3 * C));
   QB_TRY(c->ws.get(&lstm_ws, "lstm_ws", (size_t)qb_lstm_tc_workspace_bytes(B, C)));
-  const bool tc_att = !pa;
-  if (tc_att) QB_TRY(c->ws.get(&att_ws, "att_ws", (size_t)qb_attention_tc_workspace_bytes(B, F, heads)));
+  // tcgen05 attention (attention_umma.cu) in both precision policies; QB_ATTENTION=legacy keeps the round-1 kernels (mma.sync flash
+  // attention for the single-pass policy, fp32 SIMT for the split one) for A/B runs
+  static const bool legacy = [] { const char* e = getenv("QB_ATTENTION"); return e && !strcmp(e, "legacy"); }();
+  const bool tc_att = legacy && !pa;
+  if (!legacy) QB_TRY(c->ws.get(&att_ws, "att5_ws", (size_t)qb_attention_umma_workspace_bytes(B, F, heads, hd, pa ? 1 : 0)));
+  else if (tc_att) QB_TRY(c->ws.get(&att_ws, "att_ws", (size_t)qb_attention_tc_workspace_bytes(B, F, heads)));
   const float *rc, *rs;
   QB_TRY(rope_tables(c, (int)F, hd, &rc, &rs));
   for (const TfLayerW& L : layers) {
@@ -525,7 +529,8 @@ static int run_transformer(qb_codec* c, const std::vector<TfLayerW>& layers, flo
     QB_TRY(lin(t_a, M, C, L.wih, 4 * C).bias(L.b_ih).out32(xp, 4 * C, M, 0).run(st));
     QB_TRY(qb_lstm_tc(xp, (const qb_half*)L.whh_perm, c->lstm_u, B, F, C, (qb_half*)t_b.hi, (qb_half*)t_b.lo, lstm_ws, st));
     QB_TRY(lin(t_b, M, C, L.wqkv, 3 * C).bias(L.bqkv).out32(qkv, 3 * C, M, 0).run(st));
-    if (tc_att) QB_TRY(qb_attention_tc(qkv, B, F, heads, rc, rs, (qb_half*)t_a.hi, (qb_half*)t_a.lo, att_ws, st));
+    if (!legacy) QB_TRY(qb_attention_umma(qkv, B, F, heads, hd, rc, rs, (qb_half*)t_a.hi, (qb_half*)t_a.lo, pa ? 1 : 0, att_ws, st));
+    else if (tc_att) QB_TRY(qb_attention_tc(qkv, B, F, heads, rc, rs, (qb_half*)t_a.hi, (qb_half*)t_a.lo, att_ws, st));
     else QB_TRY(qb_attention_hd(qkv, B, F, heads, hd, rc, rs, (qb_half*)t_a.hi, (qb_half*)t_a.lo, st));
     QB_TRY(lin(t_a, M, C, L.wo, C).residual(x, C, M, 0).out32(x, C, M, 0).run(st));
     QB_TRY(qb_rmsnorm(x, L.post_w, 1e-6f, M, C, nullptr, (qb_half*)t_m.hi, (qb_half*)t_m.lo, st));

@@ -20,6 +20,7 @@ layers run on the tcgen05 GEMMs (3-term split) + the fp32 attention kernel.  No 
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -331,6 +332,8 @@ class SSLFrontEnd(nn.Module):
         t32 = self._buf("t32", (M, H))
         cos, sin = self._identity_rope(Tf, hd)
         wavlm = c.get("kind") == "wavlm"
+        umma = (not wavlm) and hd in (64, 128) and os.environ.get("QB_ATTENTION", "umma") != "legacy"
+        att_ws = self._buf("att5_ws", (ops.attention_umma_workspace_bytes(B, Tf, heads, hd, True),), torch.uint8) if umma else None
         if wavlm:
             rel_table = self._rel_table(Tf)
             gate = self._buf("gate", (B, heads, Tf))
@@ -340,6 +343,8 @@ class SSLFrontEnd(nn.Module):
             if wavlm:        # gated relative position bias from the layer INPUT (WavLMAttention.forward)
                 ops.wavlm_gate(xs, B, Tf, heads, hd, L["gru_w"], L["gru_b"], L["gru_c"], gate)
                 ops.attention_relbias(qkv, B, Tf, heads, hd, rel_table, gate, att)
+            elif umma:       # tcgen05 attention, split precision (csrc/attention_umma.cu)
+                ops.attention_umma(qkv, B, Tf, heads, hd, cos, sin, att, att_ws)
             else:
                 ops.attention_hd(qkv, B, Tf, heads, hd, cos, sin, att)
             ops.gemm(att, L["wo"], H, a_batch=1, a_rows_per_batch=M, a_ld=H, m_per_batch=M, bias=L["bo"],
