@@ -124,3 +124,54 @@ def test_h15_taps_vs_oracle_and_reference_surface(lib):
     assert cfg == {k: v for k, v in H15.items()}
     full = CodecH15(y["encoder_config"], y["decoder_config"], y["quantizer_config"], y["adaptive_config"])
     assert set(full.state_dict()) == set(o15.param_specs(o15.H15))
+
+
+def test_h15_bench_shape_vs_oracle(lib):
+    """the shipped config at the bench leg's clip length (10 s -> 250 frames, T + G ~ 350 rows per aggregator sequence), 2 clips,
+    bench-style inputs, against the oracle on the same weights: every float tap < 1e-3, grouping identical, indices audited"""
+    from oracle import adaptive as oad
+    from oracle import hcodec15 as o15
+    from oracle.make_golden_h15 import synth
+    from oracle.parity import audit_codes
+    from unified_audio_b200.codec_h15 import CodecH15
+    c = o15.H15
+    sd = o15.make_state_dict(c, 31)
+    m = CodecH15(precision="mixed", _cfg={k: v for k, v in c.items() if k != "layer_scale"})
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    B, N = 2, 250
+    wav, feat = synth(c, B, N, 32)
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    otaps, gtaps = {}, {}
+    oa, osem = o15.codec_encode(sd, c, wav, feat, otaps)
+    out = m.encode(wav.cuda(), feat.cuda(), taps=gtaps)
+    torch.cuda.synchronize()
+    align = otaps["align"]
+    assert torch.equal(gtaps["seg"].cpu().long(), align.argmax(1)), "grouping differs from the oracle"
+    G = align.shape[1]
+    print(f"[h15 bench shape] groups per clip {otaps['n_groups'].tolist()} of {N} frames; sequences of {N + G} rows")
+    for k in ("enc.out", "sem.out", "sem_agg.layer0", "sem_agg.layer31", "ac_agg.layer31", "sem_agg.out", "ac_agg.out"):
+        e = rel(gtaps[k], otaps[k])
+        print(f"  [h15 bench shape] tap {k}: {e:.2e}")
+        assert e < TOL
+    K, nq = c["codebook_size"], c["nq"]
+    rows = lambda t: t.double().cpu().transpose(1, 2).reshape(B * G, -1)
+    for tag, got, want, qname, key in (("acoustic", out["acoustic_codes"], oa, "quantizer", "ac_agg.out"),
+                                       ("semantic", out["semantic_codes"], osem, "semantic_quantizer", "sem_agg.out")):
+        gp, gl = oad.extract_lengths(got.cpu(), K)
+        wp, wl = oad.extract_lengths(want, K)
+        assert torch.equal(gl, wl)
+        a = audit_codes(gp, wp, rows(gtaps[key]), rows(otaps[key]), _codebooks(sd, qname, nq))
+        print(f"[h15 bench shape] {tag}: {a}")
+        assert a["explained"] and a["index_match_rate"] > 0.97
+    dt_o, dt_g = {}, {}
+    ref = o15.codec_decode(sd, c, oa, osem, dt_o)
+    rec = m.decode(oa.cuda(), osem.cuda(), taps=dt_g)
+    torch.cuda.synchronize()
+    for k in ("bottleneck.layer0", "bottleneck.out", "dec.tf", "dec.post"):
+        e = rel(dt_g[k], dt_o[k])
+        print(f"  [h15 bench shape] tap {k}: {e:.2e}")
+        assert e < TOL
+    e_wav = rel(rec, ref)
+    print(f"[h15 bench shape] wav rel {e_wav:.2e}")
+    assert rec.shape == ref.shape == (B, N * 640) and e_wav < TOL

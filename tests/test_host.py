@@ -61,6 +61,32 @@ def test_oracle_h1_reproduces_reference_golden():
     assert mine == {k: v for k, v in ref.items() if not k.startswith("semantic_decoder.")}
 
 
+def test_oracle_h15_reproduces_reference_golden():
+    """H-Codec-1.5 adaptive codec: the oracle against the outputs of the reference's own modules at the shipped widths
+    (fewer layers: tests/golden/h15_shallow.npz; the 32-layer stacks are pinned by oracle/make_golden_h15.py -> h15_pinning_report.json)"""
+    from oracle import hcodec15 as o15
+    from oracle.make_golden_h15 import synth
+    z = np.load(os.path.join(GOLD, "h15_shallow.npz"))
+    meta = json.loads(str(z["meta"]))
+    c = o15.h15_shallow()
+    sd = o15.make_state_dict(c, meta["seed_w"])
+    wav, feat = synth(c, meta["batch"], meta["frames"], meta["seed_x"])
+    taps = {}
+    ac, sc = o15.codec_encode(sd, c, wav, feat, taps)
+    assert torch.equal(taps["align"], torch.from_numpy(z["align"]).float()) and torch.equal(taps["n_groups"], torch.from_numpy(z["n_groups"]))
+    assert torch.equal(ac, torch.from_numpy(z["acoustic_codes"])) and torch.equal(sc, torch.from_numpy(z["semantic_codes"]))
+    assert int((ac < 0).sum()) > 0, "the fixture must contain padded groups (negative length-packed indices)"
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    assert rel(taps["sem_agg.out"], torch.from_numpy(z["sem_tok"])) < 1e-5 and rel(taps["ac_agg.out"], torch.from_numpy(z["ac_tok"])) < 1e-5
+    rec = o15.codec_decode(sd, c, ac, sc)
+    assert rec.shape == tuple(z["wav_rec"].shape) and rel(rec, torch.from_numpy(z["wav_rec"])) < 1e-5
+    rep = json.load(open(os.path.join(GOLD, "h15_pinning_report.json")))
+    full = [r for r in rep["reports"] if r["name"] == "full"][0]
+    assert full["acoustic_codes_equal"] and full["semantic_codes_equal"] and full["rec_rel"] < 2e-5
+    from unified_audio_b200.codec_h15 import CodecH15
+    assert set(CodecH15().state_dict()) == set(o15.param_specs(o15.H15))
+
+
 def test_oracle_rvq_self_checks():
     """get_output_from_indices(indices) == returned quantized bit-for-bit; fp64 audit agrees on safe margins;
     explicit-recurrence LSTM == ATen LSTM."""
