@@ -9,9 +9,8 @@ call shapes:
         FlexiCodec._deaggregate_features_from_token_lengths   modeling_flexicodec_new.py:1007-1041
     deaggregate(grouped [B,D,G], alignment [B,G,T]) -> [B,D,T]                       modeling_flexicodec_new.py:970-1004
 
-The rest of H-Codec-1.5 (the mimi `ProjectedTransformer` aggregators / bottleneck: 96 transformer layers with a 16-frame local
-context, head_dim 128) is not built; the SEANet encoder, the RVQ and the decoder blocks it shares with H-Codec-1.0 are
-(`codec_h1.py`).  No PyTorch / CPU fallback."""
+The codec that uses them (query-token aggregators, bottleneck transformer, H-Codec-1.0 blocks) is `codec_h15.CodecH15`.
+No PyTorch / CPU fallback."""
 from __future__ import annotations
 
 import ctypes as C
