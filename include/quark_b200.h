@@ -202,11 +202,13 @@ int qb_attention_tc(const float* qkv, int64_t B, int64_t T, int32_t heads, const
                     const float* rope_sin, qb_half* out_hi, qb_half* out_lo, void* workspace, void* stream);
 /* The same attention on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, TMA-fed operands; csrc/attention_umma.cu):
  * head_dim 64 or 128, any L; split = 0: single-pass fp16 operands, split = 1: fp16 hi + lo operands for both contractions (3 passes,
- * fp32-grade).  q is scaled by head_dim^-0.5; rope tables [L, head_dim] in the rotate-half layout.  workspace: 128-byte aligned,
+ * fp32-grade); causal = 1: query t attends keys <= t (the AR-LM's teacher-forced / prefill attention, U/model/llm/llm.py:195-216).
+ * q is scaled by head_dim^-0.5; rope tables [L, head_dim] in the rotate-half layout.  workspace: 128-byte aligned,
  * qb_attention_umma_workspace_bytes(...) bytes (the fp16 operand planes a prep launch writes).  out_lo may be NULL. */
 int64_t qb_attention_umma_workspace_bytes(int64_t B, int64_t L, int32_t heads, int32_t head_dim, int32_t split);
 int qb_attention_umma(const float* qkv, int64_t B, int64_t L, int32_t heads, int32_t head_dim, const float* rope_cos,
-                      const float* rope_sin, qb_half* out_hi, qb_half* out_lo, int32_t split, void* workspace, void* stream);
+                      const float* rope_sin, qb_half* out_hi, qb_half* out_lo, int32_t split, int32_t causal, void* workspace,
+                      void* stream);
 /* Single-layer LSTM recurrence (encoder_modules/transformer.py:115,133): xp [B,T,4H] fp32 already
  * holds x W_ih^T + b_ih + b_hh; w_hh planes [4H, H]; output h planes [B,T,H].
  * workspace: qb_lstm_workspace_bytes(B,H). */

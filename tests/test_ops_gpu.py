@@ -213,6 +213,15 @@ def test_attention_umma(lib, D, split, B, T, H):
     ops.attention_hd(qkv, B, T, H, D, cos, sin, simt)
     torch.cuda.synchronize()
     assert relerr(got, planes_ref(simt)) < (2e-5 if split else 3e-3)
+    # causal mode (the AR-LM's prefill / teacher-forced attention): key tiles past the diagonal are skipped, the diagonal tiles masked
+    ops.attention_umma(qkv, B, T, H, D, cos, sin, out, ws, causal=True)
+    torch.cuda.synchronize()
+    mask = torch.ones(T, T, dtype=torch.bool, device=DEV).tril()
+    attc = torch.softmax((q @ k.transpose(2, 3) * D ** -0.5).masked_fill(~mask, float("-inf")), -1)
+    refc = (attc @ v).transpose(1, 2).reshape(B, T, H * D)
+    ec = relerr(planes_ref(out) if split else out.hi.double(), refc)
+    print(f"   causal: relerr {ec:.2e}")
+    assert ec < (2e-5 if split else 3e-3)
 
 
 @pytest.mark.parametrize("B,T,H", [(2, 9, 256), (3, 20, 512), (5, 12, 1536), (70, 6, 512), (130, 5, 256)])

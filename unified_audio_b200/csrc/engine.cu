@@ -529,7 +529,7 @@ static int run_transformer(qb_codec* c, const std::vector<TfLayerW>& layers, flo
     QB_TRY(lin(t_a, M, C, L.wih, 4 * C).bias(L.b_ih).out32(xp, 4 * C, M, 0).run(st));
     QB_TRY(qb_lstm_tc(xp, (const qb_half*)L.whh_perm, c->lstm_u, B, F, C, (qb_half*)t_b.hi, (qb_half*)t_b.lo, lstm_ws, st));
     QB_TRY(lin(t_b, M, C, L.wqkv, 3 * C).bias(L.bqkv).out32(qkv, 3 * C, M, 0).run(st));
-    if (!legacy) QB_TRY(qb_attention_umma(qkv, B, F, heads, hd, rc, rs, (qb_half*)t_a.hi, (qb_half*)t_a.lo, pa ? 1 : 0, att_ws, st));
+    if (!legacy) QB_TRY(qb_attention_umma(qkv, B, F, heads, hd, rc, rs, (qb_half*)t_a.hi, (qb_half*)t_a.lo, pa ? 1 : 0, 0, att_ws, st));
     else if (tc_att) QB_TRY(qb_attention_tc(qkv, B, F, heads, rc, rs, (qb_half*)t_a.hi, (qb_half*)t_a.lo, att_ws, st));
     else QB_TRY(qb_attention_hd(qkv, B, F, heads, hd, rc, rs, (qb_half*)t_a.hi, (qb_half*)t_a.lo, st));
     QB_TRY(lin(t_a, M, C, L.wo, C).residual(x, C, M, 0).out32(x, C, M, 0).run(st));
@@ -1147,12 +1147,18 @@ static int lm_layers_prefill(qb_lm* m, float* x, int64_t B, int64_t L, qb_kv* kv
   QB_TRY(m->ws.planes(&hid, "hid", (size_t)M * I, true));
   QB_TRY(m->ws.f32(&qkv, "qkv", (size_t)M * 3 * H));
   QB_TRY(m->ws.f32(&q32, "q32", (size_t)M * H));
+  // prefill from an empty cache: causal tcgen05 attention over the qkv rows (attention_umma.cu); a continuation reads the cache
+  static const bool legacy_att = [] { const char* e = getenv("QB_ATTENTION"); return e && !strcmp(e, "legacy"); }();
+  const bool umma = pos0 == 0 && !legacy_att;
+  void* att_ws = nullptr;
+  if (umma) QB_TRY(m->ws.get(&att_ws, "att5_ws", (size_t)qb_attention_umma_workspace_bytes(B, L, heads, 64, 1)));
   for (int i = 0; i < m->cfg.layers; ++i) {
     const LmLayerW& w = m->layers[i];
     QB_TRY(qb_rmsnorm(x, w.in_w, 1e-6f, M, H, nullptr, (qb_half*)t1.hi, (qb_half*)t1.lo, st));
     QB_TRY(lin(t1, M, H, w.wqkv, 3 * H).out32(qkv, 3 * H, M, 0).run(st));
     QB_TRY(qb_lm_qkv_prep(qkv, B, L, heads, pos0, m->rcos, m->rsin, q32, kv->k[i], kv->v[i], kv->Lmax, st));
-    QB_TRY(qb_lm_flash_attn(q32, kv->k[i], kv->v[i], B, L, heads, pos0, kv->Lmax, (qb_half*)t1.hi, (qb_half*)t1.lo, st));
+    if (umma) QB_TRY(qb_attention_umma(qkv, B, L, heads, 64, m->rcos, m->rsin, (qb_half*)t1.hi, (qb_half*)t1.lo, 1, 1, att_ws, st));
+    else QB_TRY(qb_lm_flash_attn(q32, kv->k[i], kv->v[i], B, L, heads, pos0, kv->Lmax, (qb_half*)t1.hi, (qb_half*)t1.lo, st));
     QB_TRY(lin(t1, M, H, w.wo, H).residual(x, H, M, 0).out32(x, H, M, 0).run(st));
     QB_TRY(qb_rmsnorm(x, w.post_w, 1e-6f, M, H, nullptr, (qb_half*)t1.hi, (qb_half*)t1.lo, st));
     QB_TRY(lin(t1, M, H, w.wgu, 2 * I).act(QB_ACT_SWIGLU).outp(hid, I, M, 0).run(st));

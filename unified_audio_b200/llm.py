@@ -190,34 +190,48 @@ class LLM_SFT(nn.Module):
 
     # ------------------------------------------------------------------ transformer stack
     def _prefill(self, x: torch.Tensor, B: int, L: int, cache: StaticKVCache):
-        """x [B*L, hidden] fp32, updated in place by the 12 layers; K/V written at cache.length.."""
+        """x [B*L, hidden] fp32, updated in place by the 12 layers; K/V written at cache.length..  cache None = a teacher-forced
+        forward that nobody will decode from: no KV cache is allocated or written (tcgen05 attention only)."""
         W = self._prepare()
         H, heads, inter, M = self.hidden, self.heads, 4 * self.hidden, B * L
-        pos0 = cache.length
-        if pos0 + L > cache.Lmax:
-            raise ValueError("KV cache too small")
-        if cache.B != B or cache.heads != heads or cache.layers != self.n_layers:
-            raise ValueError(f"KV cache built for batch {cache.B} x {cache.heads} heads x {cache.layers} layers, "
-                             f"got batch {B} x {heads} heads x {self.n_layers} layers")
+        pos0 = cache.length if cache is not None else 0
+        if cache is not None:
+            if pos0 + L > cache.Lmax:
+                raise ValueError("KV cache too small")
+            if cache.B != B or cache.heads != heads or cache.layers != self.n_layers:
+                raise ValueError(f"KV cache built for batch {cache.B} x {cache.heads} heads x {cache.layers} layers, "
+                                 f"got batch {B} x {heads} heads x {self.n_layers} layers")
         self._ensure_rope(pos0 + L)
         W = self._w
         t1 = self._planes("t1", (M, H))
         hid = self._planes("hid", (M, inter))
         qkv = self._buf("qkv", (M, 3 * H))
-        q16 = self._buf("q32", (B, heads, L, 64))
+        q16 = self._buf("q32", (B, heads, L, 64)) if cache is not None else None
         xm = rowmap(x, H, M, 0)
         lin = lambda a, w, n, K, **kw: ops.gemm(a, w, n, a_batch=1, a_rows_per_batch=M, a_ld=K, m_per_batch=M, **kw)
+        # a prefill from an empty cache (every call of llm_forward / forward / generate) attends within its own L positions: the causal
+        # tcgen05 attention (csrc/attention_umma.cu) reads the qkv GEMM's output directly; lm_qkv_prep still fills the fp32 KV cache for
+        # the decode steps.  A continuation (pos0 > 0) keeps the cache-reading mma.sync kernel.
+        umma = pos0 == 0 and os.environ.get("QB_ATTENTION", "umma") != "legacy"
+        if cache is None and not umma:
+            raise RuntimeError("cache-less prefill needs the tcgen05 attention path")
+        att_ws = self._buf("att5_ws", (ops.attention_umma_workspace_bytes(B, L, heads, 64, True),), torch.uint8) if umma else None
         for i, Lw in enumerate(W["layers"]):
             ops.rmsnorm(x, Lw["in_w"], M, H, t1)
             lin(t1, Lw["wqkv"], 3 * H, H, out_f32=rowmap(qkv, 3 * H, M, 0))
-            ops.lm_qkv_prep(qkv, B, L, heads, pos0, W["cos"], W["sin"], q16, cache.k[i], cache.v[i], cache.Lmax)
-            ops.lm_flash_attn(q16, cache.k[i], cache.v[i], B, L, heads, pos0, cache.Lmax, t1)
+            if cache is not None:
+                ops.lm_qkv_prep(qkv, B, L, heads, pos0, W["cos"], W["sin"], q16, cache.k[i], cache.v[i], cache.Lmax)
+            if umma:
+                ops.attention_umma(qkv, B, L, heads, 64, W["cos"], W["sin"], t1, att_ws, split=True, causal=True)
+            else:
+                ops.lm_flash_attn(q16, cache.k[i], cache.v[i], B, L, heads, pos0, cache.Lmax, t1)
             lin(t1, Lw["wo"], H, H, residual=xm, out_f32=xm)
             ops.rmsnorm(x, Lw["post_w"], M, H, t1)
             lin(t1, Lw["wgu"], 2 * inter, H, act=ACT_SWIGLU, out_planes=hid, out_planes_map=(inter, M, 0))
             lin(hid, Lw["wd"], H, inter, residual=xm, out_f32=xm)
-        cache.length = pos0 + L
-        cache.pos.fill_(cache.length)
+        if cache is not None:
+            cache.length = pos0 + L
+            cache.pos.fill_(cache.length)
 
     def _decode_layers(self, x: torch.Tensor, B: int, cache: StaticKVCache):
         W = self._prepare()
@@ -237,6 +251,14 @@ class LLM_SFT(nn.Module):
         W = self._prepare()
         B, L, H = inputs_embeds.shape
         cache = past_key_values
+        if cache is None and not use_cache and os.environ.get("QB_ATTENTION", "umma") != "legacy":
+            # teacher-forced forward (LLM_SFT.forward, llm_sft.py:93-135): nothing decodes from it, so no KV cache at all
+            self._ensure_rope(L)
+            x = inputs_embeds.float().reshape(B * L, H).contiguous().clone()
+            self._prefill(x, B, L, None)
+            out = torch.empty(B * L, H, device=x.device)
+            ops.rmsnorm(x, self._w["norm"], B * L, H, out_f32=out)
+            return LMOutput(out.reshape(B, L, H), None)
         if cache is None:
             extra = (max_new_tokens if max_new_tokens is not None else 1024) if use_cache else 0
             cache = StaticKVCache(self.n_layers, B, self.heads, max(64, -(-(L + extra) // 64) * 64), self._dev())

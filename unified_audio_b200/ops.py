@@ -223,11 +223,11 @@ def attention_umma_workspace_bytes(B, L, heads, head_dim, split):
     return int(_lib.load().qb_attention_umma_workspace_bytes(B, L, heads, head_dim, int(bool(split))))
 
 
-def attention_umma(qkv, B, L, heads, head_dim, rope_cos, rope_sin, out: Planes, workspace, split=None):
+def attention_umma(qkv, B, L, heads, head_dim, rope_cos, rope_sin, out: Planes, workspace, split=None, causal=False):
     """tcgen05 attention (head_dim 64 / 128); split defaults to whether `out` carries a lo plane"""
     split = (out.lo is not None) if split is None else split
     _lib.check(_lib.load().qb_attention_umma(_p(qkv), B, L, heads, head_dim, _p(rope_cos), _p(rope_sin), _p(out.hi), _p(out.lo),
-                                             int(bool(split)), _p(workspace), _stream()))
+                                             int(bool(split)), int(bool(causal)), _p(workspace), _stream()))
 
 
 def lstm_workspace_bytes(B, H):
