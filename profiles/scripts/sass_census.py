@@ -33,3 +33,21 @@ for name, c in rows:
 tc = [n for n, c in kern.items() if c["UTCHMMA"]]
 print(f"\n{len(kern)} kernels; {len(tc)} issue tcgen05.mma; {sum(1 for c in kern.values() if c['HMMA'])} use legacy mma.sync "
       "(the LM decode / prefill-continuation kernels, the round-1 attention kept for A/B, the cross-check LSTM).")
+
+# ---- excerpts: every tensor-core / TMEM / TMA instruction of the tcgen05 kernels, verbatim (profiles/r02_sass_excerpts.txt)
+if len(sys.argv) > 1:
+    pat = re.compile(r"\b(UTCHMMA|UTCCP|LDTM|STTM|UTMALDG|UBLKCP|UTCBAR|UTCATOMSWS)\b")
+    with open(sys.argv[1], "w") as f:
+        f.write("SASS excerpts (cuobjdump -sass libquark_b200.so): every tcgen05 / TMEM / TMA instruction of the kernels that issue tcgen05.mma\n")
+        cur, keep, lines = None, False, []
+        for line in txt.splitlines():
+            m = re.match(r"\s*Function : (\S+)", line)
+            if m:
+                cur = m.group(1)
+                keep = kern[cur]["UTCHMMA"] > 0
+                if keep:
+                    d = re.sub(r"\((int|bool|unsigned int)\)", "", demangle(cur))
+                    f.write("\n== " + re.sub(r"\(.*", "", d) + f"  ({kern[cur]['_n']} instructions)\n")
+                continue
+            if keep and pat.search(line):
+                f.write(re.sub(r"\s+/\* 0x[0-9a-f]+ \*/\s*$", "", line.rstrip()) + "\n")

@@ -417,7 +417,8 @@ class Codec(nn.Module):
                          out_planes_map=(Cs, Tc + 2, 1), act2=ACT_ELU if u == 0 else ACT_NONE)
             st, k = blk["stride"], blk["k"]
             pad = (k - 1) // 2
-            assert pad == 1 and (Tc + 2) % st == 0
+            if pad != 1 or (Tc + 2) % st != 0:
+                raise ValueError(f"semantic encoder: {Tc} frames cannot be strided by {st} with kernel {k} (frame count must be even)")
             Tn = (Tc + 2 * pad - k) // st + 1
             sx2 = self._buf(f"sem_x{Tn}_{bi}", (B * Tn, Cs))
             pe2 = self._planes(f"sem_pe{Tn}_{bi}", (B, Tn + 2, Cs), pc)

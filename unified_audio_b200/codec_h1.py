@@ -262,7 +262,8 @@ class CodecH1(Codec):
         E, c = W["enc"], self.c
         pc = self.policy["conv"]
         B, one, T = x.shape
-        assert one == 1
+        if one != 1:
+            raise ValueError(f"expected a mono waveform [B, 1, T], got {tuple(x.shape)}")
         if T % 640 != 0:
             raise ValueError(f"waveform length {T} must be a multiple of 640 (hop 320 x final stride 2)")
         x = x.float().reshape(B, T, 1).contiguous()
