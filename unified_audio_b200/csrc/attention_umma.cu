@@ -228,9 +228,11 @@ fa5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
       // Whichever is ready goes next: S_{i} into S buffer i & 1 (free once the softmax threads signalled p_full(i - 2), i.e. pv >= i - 1)
       // as soon as K_i has landed - it then runs under the softmax of tile i - 1 - or P.V_j once P_j and V_j are there.
       int si = 0, pv = 0;
+      unsigned spins = 0;
       while (pv < n_tiles) {
-        if (si < n_tiles && si <= pv + 1 && mbar_test(k_full + (si & 1), (si >> 1) & 1)) { issue_s(si); ++si; }
-        if (pv < si && mbar_test(p_full, pv & 1) && mbar_test(v_full, pv & 1)) { issue_pv(pv); ++pv; }
+        if (++spins > (1u << 26)) __trap();      // a mis-programmed pipeline traps instead of hanging the GPU box (cf. mbar_wait)
+        if (si < n_tiles && si <= pv + 1 && mbar_test(k_full + (si & 1), (si >> 1) & 1)) { issue_s(si); ++si; spins = 0; }
+        if (pv < si && mbar_test(p_full, pv & 1) && mbar_test(v_full, pv & 1)) { issue_pv(pv); ++pv; spins = 0; }
       }
     }
   } else {
