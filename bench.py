@@ -518,7 +518,7 @@ def bench_h15(args, ctx):
         return out, model.decode(out["acoustic_codes"], out["semantic_codes"])
     # one counted step: GEMM FLOPs as the algorithm states them (2 M N K, one pass) + attention (4 L^2 C per layer and item)
     flops = [0.0]
-    real_gemm, real_att, real_att_tc = ops.gemm, ops.attention_hd, ops.attention_tc
+    real_gemm, real_att, real_att_tc, real_att5 = ops.gemm, ops.attention_hd, ops.attention_tc, ops.attention_umma
 
     def count_gemm(a, w, n, **kw):
         flops[0] += 2.0 * kw["a_batch"] * kw["m_per_batch"] * n * kw.get("taps", 1) * (kw.get("a_cols") or kw["a_ld"])
@@ -531,11 +531,14 @@ def bench_h15(args, ctx):
     def count_att_tc(qkv, B_, T_, heads, *a):
         flops[0] += 4.0 * B_ * T_ * T_ * heads * 64
         return real_att_tc(qkv, B_, T_, heads, *a)
-    ops.gemm, ops.attention_hd, ops.attention_tc = count_gemm, count_att, count_att_tc
+    def count_att5(qkv, B_, T_, heads, hd, *a, **kw):
+        flops[0] += 4.0 * B_ * T_ * T_ * heads * hd
+        return real_att5(qkv, B_, T_, heads, hd, *a, **kw)
+    ops.gemm, ops.attention_hd, ops.attention_tc, ops.attention_umma = count_gemm, count_att, count_att_tc, count_att5
     try:
         out, rec = step()
     finally:
-        ops.gemm, ops.attention_hd, ops.attention_tc = real_gemm, real_att, real_att_tc
+        ops.gemm, ops.attention_hd, ops.attention_tc, ops.attention_umma = real_gemm, real_att, real_att_tc, real_att5
     torch.cuda.synchronize()
     from unified_audio_b200 import adaptive
     _, lens = adaptive.extract_lengths(out["acoustic_codes"], model.codebook_size)
@@ -547,9 +550,64 @@ def bench_h15(args, ctx):
     peaks = load_peaks()
     tf = ctx.world * flops[0] / (ms * 1e-3) / 1e12
     n_samples = B * T50 * 320
+    # e2e: inputs from pinned host memory, length-packed codes + waveform read back, every step
+    wav_h, feat_h = wav.cpu().pin_memory(), feat.cpu().pin_memory()
+    out_h = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in (out["acoustic_codes"], out["semantic_codes"], rec)]
+
+    def e2e_step():
+        o, r = None, None
+        w, f = wav_h.to(dev, non_blocking=True), feat_h.to(dev, non_blocking=True)
+        o = model.encode(w, f)
+        r = model.decode(o["acoustic_codes"], o["semantic_codes"])
+        for dst, src in zip(out_h, (o["acoustic_codes"], o["semantic_codes"], r)):
+            if dst.shape == src.shape:
+                dst.copy_(src, non_blocking=True)
+            else:                                   # the group count G of a batch is data dependent: same batch, same G
+                dst.resize_(src.shape).copy_(src, non_blocking=True)
+    e2e_step()
+    ms_e2e = ctx.timed(e2e_step, 2)
+    extra = {}
+    if ctx.world == 1 and not args.no_cpu_baseline:
+        # the oracle (CPU restatement of the reference, same weights) on clip 0 alone; the GPU path re-run on that clip alone (the T + G padding of a
+        # batch depends on its largest group count, so a clip is only comparable with itself at batch 1)
+        from oracle import adaptive as oad
+        from oracle import hcodec15 as o15
+        from oracle.parity import audit_codes
+        sd_cpu = {k: v.detach().float().cpu() if v.is_floating_point() else v.detach().cpu() for k, v in model.state_dict().items()}
+        c = dict(o15.H15)
+        n = cpu_threads()
+        torch.set_num_threads(n)
+        w1, f1 = wav[:1].cpu(), feat[:1].cpu()
+        t0 = time.perf_counter()
+        otaps = {}
+        oa, os_ = o15.codec_encode(sd_cpu, c, w1, f1, otaps)
+        ref = o15.codec_decode(sd_cpu, c, oa, os_)
+        dt = time.perf_counter() - t0
+        gtaps = {}
+        go = model.encode(wav[:1], feat[:1], taps=gtaps)
+        grec = model.decode(oa.to(dev), os_.to(dev))
+        relf = lambda a, b: float((a.double().cpu() - b.double()).abs().max() / b.double().abs().max())
+        G1 = oa.shape[-1]
+        rows = lambda t: t.double().cpu().transpose(1, 2).reshape(G1, -1)
+        par = dict(sample="clip 0 of the timed batch, alone, vs the oracle (same weights)", grouping_identical=bool(torch.equal(gtaps["seg"].cpu().long(), otaps["align"].argmax(1))),
+                   sem_tok_rel=relf(gtaps["sem_agg.out"], otaps["sem_agg.out"]), ac_tok_rel=relf(gtaps["ac_agg.out"], otaps["ac_agg.out"]), wav_rel=relf(grec, ref))
+        K = model.codebook_size
+        for tag, got, want, key, q in (("acoustic", go["acoustic_codes"], oa, "ac_agg.out", "quantizer"), ("semantic", go["semantic_codes"], os_, "sem_agg.out", "semantic_quantizer")):
+            gp, gl = oad.extract_lengths(got.cpu(), K)
+            wp, wl = oad.extract_lengths(want, K)
+            cb = torch.stack([sd_cpu[f"{q}.layers.{i}._codebook.embed"][0] for i in range(c["nq"])], 0)
+            a = audit_codes(gp, wp, rows(gtaps[key]), rows(otaps[key]), cb) if torch.equal(gl, wl) else dict(explained=False)
+            par[tag] = {k: a.get(k) for k in ("tokens", "tokens_differing", "index_match_rate", "worst_gap", "worst_reach", "explained")}
+        par["ok"] = bool(par["grouping_identical"] and par["sem_tok_rel"] < 1e-3 and par["ac_tok_rel"] < 1e-3 and par["wav_rel"] < 1e-3
+                         and par["acoustic"]["explained"] and par["semantic"]["explained"])
+        extra = dict(parity=par, cpu_baseline=dict(value=T50 * 320 / dt, unit=UNIT, cores=n, host_cores=host_cores(), kind="port",
+                                                   sample=f"1 clip x {T50 / 50:g} s encode + decode ({dt:.1f} s), oracle port of the reference's PyTorch CPU path, same weights, {n} threads"))
+    h2d = wav_h.numel() * 4 + feat_h.numel() * 4
+    d2h = sum(o.numel() * o.element_size() for o in out_h)
     del model
     torch.cuda.empty_cache()
-    return dict(metric="hcodec15_adaptive_encode_decode_samples_per_s", value=ctx.world * n_samples / (ms * 1e-3), unit=UNIT, ms_per_step=ms,
+    return dict(e2e=dict(value=ctx.world * n_samples / (ms_e2e * 1e-3), unit=UNIT, ms_per_step=ms_e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h), **extra,
+                metric="hcodec15_adaptive_encode_decode_samples_per_s", value=ctx.world * n_samples / (ms * 1e-3), unit=UNIT, ms_per_step=ms,
                 n_gpus=ctx.world, scaling="weak",
                 config=dict(workload=f"HCodec-1.5 adaptive (config_adaptive_v3) batch={B} x {T50 / 50:g} s @16 kHz encode + decode, threshold 0.6",
                             batch_per_gpu=B, frames_25hz=T50 // 2, tokens_per_clip_mean=float(n_tok.mean()), tokens_per_clip_max=int(n_tok.max()),
