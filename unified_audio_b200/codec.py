@@ -598,6 +598,48 @@ class GraphedCall:
         self.graph.replay()
         return self.outputs
 
+    # ------------------------------------------------------------------ streaming host I/O
+    def stream(self, host_inputs, host_outputs):
+        """One step of a serving loop with HOST tensors on both sides, copies overlapped with compute: the H2D copy of this step's
+        (pinned) inputs runs on a copy stream into a staging buffer while the previous step still computes; the step itself is a
+        device-to-device move into the graph's static inputs + the replay + a device-to-device move of its outputs into a second
+        staging buffer, from which the copy stream drains them into `host_outputs` (pinned) under the next step.  Call
+        `finish()` (or torch.cuda.synchronize()) before reading `host_outputs` of the last step."""
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_io", None) is None:
+            outs = self.outputs if isinstance(self.outputs, (tuple, list)) else (self.outputs,)
+            # two copy streams: on one, the H2D of step i + 1 would queue behind the D2H of step i, which waits for step i's compute
+            self._io = dict(stream=torch.cuda.Stream(), d2h_stream=torch.cuda.Stream(), in_stage=[torch.empty_like(t) for t in self.inputs],
+                            out_stage=[torch.empty_like(t) for t in outs], h2d=torch.cuda.Event(), staged=torch.cuda.Event(),
+                            consumed=torch.cuda.Event(), drained=torch.cuda.Event())
+            self._io["consumed"].record(cur)
+            self._io["drained"].record(cur)
+        io = self._io
+        with torch.cuda.stream(io["stream"]):
+            io["stream"].wait_event(io["consumed"])            # the previous step has moved its inputs out of the staging buffer
+            for dst, src in zip(io["in_stage"], host_inputs):
+                dst.copy_(src, non_blocking=True)
+            io["h2d"].record(io["stream"])
+        cur.wait_event(io["h2d"])
+        for dst, src in zip(self.inputs, io["in_stage"]):
+            dst.copy_(src, non_blocking=True)
+        io["consumed"].record(cur)
+        self.graph.replay()
+        outs = self.outputs if isinstance(self.outputs, (tuple, list)) else (self.outputs,)
+        cur.wait_event(io["drained"])                           # the previous step's outputs have left the staging buffer
+        for dst, src in zip(io["out_stage"], outs):
+            dst.copy_(src, non_blocking=True)
+        io["staged"].record(cur)
+        with torch.cuda.stream(io["d2h_stream"]):
+            io["d2h_stream"].wait_event(io["staged"])
+            for dst, src in zip(host_outputs, io["out_stage"]):
+                dst.copy_(src, non_blocking=True)
+            io["drained"].record(io["d2h_stream"])
+
+    def finish(self):
+        if getattr(self, "_io", None) is not None:
+            torch.cuda.current_stream().wait_event(self._io["drained"])
+
 
 def stft2_factors(n_fft: int):
     """n_fft = P * Q with P <= 64 and Q <= 64 (P as large as possible): 1920 -> (48, 40), 1280 -> (40, 32); None if impossible"""
