@@ -19,7 +19,6 @@ Pinned by oracle/make_golden_h15.py against the reference's own modules (tests/g
 from __future__ import annotations
 
 import math
-from collections import OrderedDict
 
 import torch
 import torch.nn.functional as F

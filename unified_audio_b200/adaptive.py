@@ -13,7 +13,6 @@ The codec that uses them (query-token aggregators, bottleneck transformer, H-Cod
 No PyTorch / CPU fallback."""
 from __future__ import annotations
 
-import ctypes as C
 
 import torch
 

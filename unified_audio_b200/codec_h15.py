@@ -31,13 +31,11 @@ import os
 from typing import Dict
 
 import torch
-from torch import nn
 
 from . import _lib, adaptive, ops
-from .codec import Codec, _Tree, PRECISION_POLICIES
-from .codec_h1 import CodecH1, H1, h1_spec
+from .codec import _Tree
+from .codec_h1 import CodecH1, H1
 from .ops import ACT_GELU, Planes, _p, _stream, rowmap
-from .rvq import ResidualVQ
 
 H15 = dict(H1, ratios=[8, 5, 4, 2], dec_dim=1024, sem_in=1024, sem_ch=1024,
            agg=dict(dim=512, heads=8, layers=32, ff=2048), bottleneck=dict(dim=1024, heads=8, layers=32, ff=2048),

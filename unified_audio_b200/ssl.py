@@ -28,7 +28,7 @@ from torch import nn
 
 from . import ops
 from .codec import _Tree, _pad_to
-from .ops import ACT_GELU, ACT_NONE, Planes, rowmap
+from .ops import ACT_GELU, Planes, rowmap
 
 HUBERT_BASE = dict(conv_dim=[512] * 7, conv_kernel=[10, 3, 3, 3, 3, 2, 2], conv_stride=[5, 2, 2, 2, 2, 2, 2], hidden=768,
                    layers=12, heads=12, ffn=3072, pos_k=128, pos_groups=16, eps=1e-5, kind="hubert")
