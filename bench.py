@@ -156,6 +156,10 @@ class Ctx:
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         self.dist = None
+        self.t0 = time.perf_counter()
+        # wall-clock budget for the optional legs (the driver's per-N limit in the scaling run is 870 s): a leg that would start
+        # after the budget is recorded as skipped instead of endangering the headline line
+        self.budget_s = float(os.environ.get("QB_BENCH_BUDGET_S", "540"))
         if self.world > 1:
             import torch.distributed as dist_
             if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -184,9 +188,36 @@ class Ctx:
             ms = float(t)
         return ms / steps
 
+    def over_budget(self):
+        """True once the invocation has used its wall-clock budget; rank 0 decides for every rank (the legs contain barriers)."""
+        over = time.perf_counter() - self.t0 > self.budget_s
+        if self.dist is not None:
+            t = torch.tensor([1 if over else 0], device=self.dev, dtype=torch.int32)
+            self.dist.broadcast(t, src=0)
+            over = bool(int(t))
+        return over
+
+    def elapsed_s(self):
+        return time.perf_counter() - self.t0
+
     def close(self):
         if self.dist is not None:
             self.dist.destroy_process_group()
+
+
+def run_leg(ctx, sec, name, fn):
+    """One optional leg of the bench line: never takes the headline down, never starts after the wall-clock budget."""
+    if ctx.over_budget():
+        sec[name] = dict(skipped=f"wall-clock budget of {ctx.budget_s:.0f} s reached after {ctx.elapsed_s():.0f} s (QB_BENCH_BUDGET_S)")
+        return
+    t0 = time.perf_counter()
+    try:
+        sec[name] = fn()
+    except Exception as e:
+        sec[name] = dict(error=repr(e))
+        torch.cuda.synchronize()
+    if isinstance(sec[name], dict):
+        sec[name]["leg_wall_s"] = round(time.perf_counter() - t0, 1)
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs (oracle port)
@@ -618,7 +649,7 @@ def bench_h15(args, ctx):
                               flops_per_step=flops[0]))
 
 
-def run_codec(args, cfg, ctx, collect_secondary):
+def run_codec(args, cfg, ctx, collect_secondary, first_legs=None):
     from unified_audio_b200 import ops
     from unified_audio_b200.parallel import gather_tokens
     world, rank, dev = ctx.world, ctx.rank, ctx.dev
@@ -809,11 +840,13 @@ def run_codec(args, cfg, ctx, collect_secondary):
     sec = None
     if collect_secondary:
         sec = {}
-        try:
-            sec["codec_b256_strong"] = bench_codec_strong(args, ctx, model, cfg, 256)
-        except Exception as e:
-            sec["codec_b256_strong"] = dict(error=repr(e))
-        try:    # SURVEY 8(d) "24 kHz sample-count" reporting shape: 240 000 samples -> pad_wav -> 241 920 (63 tokens, 252 frames)
+        if first_legs is not None:      # the AR-LM half of the metric goes before the codec's extra shapes
+            first_legs(sec)
+
+        def leg_strong():
+            return bench_codec_strong(args, ctx, model, cfg, 256)
+
+        def leg_240k():     # SURVEY 8(d) "24 kHz sample-count" reporting shape: 240 000 samples -> pad_wav -> 241 920 (63 tokens, 252 frames)
             from unified_audio_b200.ssl import pad_wav
             g24 = torch.Generator().manual_seed(2400 + rank)
             w24 = pad_wav((0.1 * torch.randn(B, 240000, generator=g24)).to(dev), 3840)
@@ -822,33 +855,31 @@ def run_codec(args, cfg, ctx, collect_secondary):
             g24c = model.graphed("roundtrip", w24, f24)
             g24c()
             ms24 = ctx.timed(lambda: g24c(), 3)
-            sec["codec_240k_samples_shape"] = dict(metric=METRIC, value=world * B * 240000 / (ms24 * 1e-3), unit=UNIT, ms_per_step=ms24,
-                                                   config=dict(workload=f"HCodec-2.0 batch={B} x 240 000 samples (padded to {w24.shape[1]}: 63 tokens, "
-                                                                        "252 frames) encode+RVQ+decode", batch_per_gpu=B),
-                                                   path_algorithmic_tflops=world * B * (w24.shape[1] // 960) * FLOP_PER_FRAME / (ms24 * 1e-3) / 1e12)
-            del g24c
-        except Exception as e:
-            sec["codec_240k_samples_shape"] = dict(error=repr(e))
-            torch.cuda.synchronize()
-        try:
-            sec["tokenize_wav_to_codes"] = bench_tokenize(args, ctx, model, cfg)
-        except Exception as e:
-            sec["tokenize_wav_to_codes"] = dict(error=repr(e))
-            torch.cuda.synchronize()
+            return dict(metric=METRIC, value=world * B * 240000 / (ms24 * 1e-3), unit=UNIT, ms_per_step=ms24,
+                        config=dict(workload=f"HCodec-2.0 batch={B} x 240 000 samples (padded to {w24.shape[1]}: 63 tokens, "
+                                             "252 frames) encode+RVQ+decode", batch_per_gpu=B),
+                        path_algorithmic_tflops=world * B * (w24.shape[1] // 960) * FLOP_PER_FRAME / (ms24 * 1e-3) / 1e12)
+
+        def leg_tokenize():
+            return bench_tokenize(args, ctx, model, cfg)
+
+        def leg_accurate():     # fp32-grade policy (every GEMM a 3-term split) beside the default
+            nonlocal graphed
+            graphed = None
+            model._ws, model._engine = {}, None
+            torch.cuda.empty_cache()
+            macc = build_codec(cfg, dev, "accurate")
+            gacc = macc.graphed("roundtrip", wav_d, feat_d)
+            gacc()
+            ms_acc = ctx.timed(lambda: gacc(), 3)
+            return dict(metric=METRIC, value=B * T / (ms_acc * 1e-3), unit=UNIT, ms_per_step=ms_acc,
+                        config=dict(precision_policy="accurate", batch_per_gpu=B))
+
+        legs = [("codec_b256_strong", leg_strong), ("codec_240k_samples_shape", leg_240k), ("tokenize_wav_to_codes", leg_tokenize)]
         if world == 1 and args.precision != "accurate":
-            try:        # fp32-grade policy (every GEMM a 3-term split) beside the default
-                del graphed
-                model._ws, model._engine = {}, None
-                torch.cuda.empty_cache()
-                macc = build_codec(cfg, dev, "accurate")
-                gacc = macc.graphed("roundtrip", wav_d, feat_d)
-                gacc()
-                ms_acc = ctx.timed(lambda: gacc(), 3)
-                sec["codec_accurate_policy"] = dict(metric=METRIC, value=B * T / (ms_acc * 1e-3), unit=UNIT, ms_per_step=ms_acc,
-                                                    config=dict(precision_policy="accurate", batch_per_gpu=B))
-                del gacc, macc
-            except Exception as e:
-                sec["codec_accurate_policy"] = dict(error=repr(e))
+            legs.append(("codec_accurate_policy", leg_accurate))
+        for name, fn in legs:
+            run_leg(ctx, sec, name, fn)
     del model
     torch.cuda.empty_cache()
     return line, sec
@@ -1054,27 +1085,30 @@ def main():
             print(json.dumps(out))
         ctx.close()
         return
-    res = run_codec(args, cfg, ctx, collect_secondary=args.workload == "all" and not args.quick)
+    lm_box = {}
+
+    def lm_first(sec):
+        # the AR-LM half of BASELINE.json's metric in the same invocation: SR B=32 (configs[2]) and TSE B=16 (configs[3]) per GPU
+        lm_box["m"] = m = build_lm(ctx.dev)
+        with_cpu = ctx.world == 1 and not args.no_cpu_baseline
+        run_leg(ctx, sec, "lm_sr", lambda: bench_lm_generate(args, ctx, m, "se", 32, with_cpu=with_cpu))
+        run_leg(ctx, sec, "lm_tse", lambda: bench_lm_generate(args, ctx, m, "tse", 16, with_cpu=with_cpu))
+
+    full = args.workload == "all" and not args.quick
+    res = run_codec(args, cfg, ctx, collect_secondary=full, first_legs=lm_first if full else None)
     if res is None:
         ctx.close()
         return
     line, sec = res
-    if args.workload == "all":
-        # the AR-LM half of BASELINE.json's metric in the same invocation: SR B=32 (configs[2]), TSE B=16 (configs[3]) per GPU,
-        # the batch-256 sweep (configs[4]) and the teacher-forced forward
-        m = build_lm(ctx.dev)
-        with_cpu = ctx.world == 1 and not args.no_cpu_baseline
-        for name, fn in (("lm_sr", lambda: bench_lm_generate(args, ctx, m, "se", 32, with_cpu=with_cpu)),
-                         ("lm_tse", lambda: bench_lm_generate(args, ctx, m, "tse", 16, with_cpu=with_cpu)),
-                         ("lm_sr_b256_strong", lambda: bench_lm_generate(args, ctx, m, "se", None, total_batch=256, steps=2)),
+    if full:
+        # the batch-256 sweep (configs[4]), the teacher-forced forward, the adaptive codec
+        m = lm_box["m"]
+        for name, fn in (("lm_sr_b256_strong", lambda: bench_lm_generate(args, ctx, m, "se", None, total_batch=256, steps=2)),
                          ("lm_forward", lambda: bench_lm_forward(args, ctx, m)),
                          ("hcodec15_adaptive", lambda: bench_h15(args, ctx))):
-            try:
-                sec[name] = fn()
-            except Exception as e:          # a secondary leg never takes the headline line down
-                sec[name] = dict(error=repr(e))
-                torch.cuda.synchronize()
+            run_leg(ctx, sec, name, fn)
         line["secondary"] = sec
+        line["bench_wall_s"] = round(ctx.elapsed_s(), 1)
     if ctx.rank == 0:
         print(json.dumps(line))
     ctx.close()

@@ -16,6 +16,7 @@ setting U/model/model.py:173).  No PyTorch / CPU fallback for the transformer st
 """
 from __future__ import annotations
 
+import copy
 from dataclasses import dataclass
 import os
 from typing import Optional
@@ -107,17 +108,23 @@ class LLM_SFT(nn.Module):
         self.decode_kernel = os.environ.get("QB_LM_DECODE", "tc")
         self.graph_steps = int(os.environ.get("QB_LM_GRAPH_STEPS", "8"))     # decode steps per replayed CUDA graph
         self._gen_state = {}
+        # generate() walks a batch in chunks of <= `chunk` sequences; `lanes` > 1 runs that many chunks CONCURRENTLY, each on its own
+        # CUDA stream with its own KV cache / workspace / captured graphs (the decode step is a chain of ~62 short dependent kernels:
+        # one chain leaves most of the GPU idle, independent chains fill it).  Tokens do not depend on either setting.
+        self.lanes = max(1, int(os.environ.get("QB_LM_LANES", "1")))
+        self.chunk = min(32, max(1, int(os.environ.get("QB_LM_CHUNK", "32"))))
+        self._lane_views = None
         self.eval()
 
     # ------------------------------------------------------------------ state
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         sd = {k: v for k, v in state_dict.items() if not k.startswith(("cond_", "rotary_emb."))}
         r = super().load_state_dict(sd, strict=strict, assign=assign)
-        self._w, self._gen_state = None, {}          # captured graphs point at the old prepared weights
+        self._w, self._gen_state, self._lane_views = None, {}, None          # captured graphs point at the old prepared weights
         return r
 
     def _apply(self, fn, *a, **k):
-        self._w, self._ws, self._gen_state = None, {}, {}
+        self._w, self._ws, self._gen_state, self._lane_views = None, {}, {}, None
         return super()._apply(fn, *a, **k)
 
     def _dev(self):
@@ -357,16 +364,56 @@ class LLM_SFT(nn.Module):
             sampling = dict(temperature=float(temperature), top_k=int(top_k), top_p=float(top_p), seed=int(seed))
         semantic_length = mix_mel.size(1)
         Ball = mix_feats.shape[0]
-        outs_g, outs_s = [], []
-        for ci, b0 in enumerate(range(0, Ball, 32)):      # decode kernels keep <= 32 sequences' rows in registers
-            sl = slice(b0, min(b0 + 32, Ball))
-            if sampling is not None:
-                sampling["call"] = ci
-            gi, si = self._generate_chunk(task_name, None if enroll_mel is None else enroll_feats[sl], mix_feats[sl],
-                                          semantic_length, global_length, use_cuda_graph, sampling)
-            outs_g.append(gi)
-            outs_s.append(si)
-        return torch.cat(outs_g, 0), torch.cat(outs_s, 0)
+        starts = list(range(0, Ball, self.chunk))         # decode kernels keep <= 32 sequences' rows in registers
+        n_lanes = min(self.lanes, len(starts))
+        outs = []
+        if n_lanes <= 1:
+            for ci, b0 in enumerate(starts):
+                sl = slice(b0, min(b0 + self.chunk, Ball))
+                if sampling is not None:
+                    sampling["call"] = ci
+                outs.append(self._generate_chunk(task_name, None if enroll_mel is None else enroll_feats[sl], mix_feats[sl],
+                                                 semantic_length, global_length, use_cuda_graph, sampling))
+        else:
+            # chunk ci runs on lane ci % n_lanes: the host enqueues one chunk after the other, the device overlaps the lanes
+            n_pos = 2 + mix_feats.shape[1] + (0 if enroll_mel is None else 1 + enroll_feats.shape[1]) + global_length + 1 + semantic_length
+            views = self._lanes(n_lanes, n_pos)
+            cur = torch.cuda.current_stream()
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            for ci, b0 in enumerate(starts):
+                sl = slice(b0, min(b0 + self.chunk, Ball))
+                view, stream = views[ci % n_lanes]
+                if sampling is not None:
+                    sampling["call"] = ci
+                if ci < n_lanes:
+                    stream.wait_event(ready)             # the inputs were produced on the caller's stream
+                with torch.cuda.stream(stream):
+                    outs.append(view._generate_chunk(task_name, None if enroll_mel is None else enroll_feats[sl], mix_feats[sl],
+                                                     semantic_length, global_length, use_cuda_graph, sampling))
+            for _, stream in views[:n_lanes]:
+                cur.wait_stream(stream)
+            for gi, si in outs:                           # allocated on a lane's stream, consumed on the caller's
+                gi.record_stream(cur)
+                si.record_stream(cur)
+        return torch.cat([o[0] for o in outs], 0), torch.cat([o[1] for o in outs], 0)
+
+    def _lanes(self, n: int, n_positions: int):
+        """Lane = (shallow view of this module with its own workspace, decode state and captured graphs; its own stream).  The
+        prepared weights and RoPE tables are shared read-only, so the tables are sized BEFORE the lanes exist (growing them
+        replaces the tensors captured graphs point at)."""
+        self._prepare()
+        self._ensure_rope(n_positions)
+        rows = self._w["rope_rows"]
+        if self._lane_views is None or self._lane_views[0] != rows:
+            self._lane_views = (rows, [])
+        lanes = self._lane_views[1]
+        while len(lanes) < n:
+            v = copy.copy(self)
+            v._ws, v._gen_state, v._lane_views = {}, {}, None
+            v.lanes = 1
+            lanes.append((v, torch.cuda.Stream(device=self._dev())))
+        return lanes
 
     def _generate_chunk(self, task_name, enroll_feats, mix_feats, semantic_length, global_length, use_graph, sampling=None):
         W = self._prepare()
