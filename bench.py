@@ -374,6 +374,8 @@ def bench_lm_generate(args, ctx, m, task, B_local, total_batch=None, with_cpu=Fa
                config=dict(workload=f"UniSE {'SR' if task == 'se' else 'TSE (enrollment prefix)'} AR-LM greedy generate: prefill {P} + 33 + 250 cached "
                                     f"steps, KV <= {P + 283}", batch=B_all, batch_per_gpu=B_local, semantic_length=T,
                            parallelism=f"dp{world} (sequences sharded, one NCCL all_gather of ids)",
+                           chunks=f"{chunks_local} chunk(s) of <= {m.chunk} sequences per GPU on {min(m.lanes, chunks_local)} concurrent lane(s) "
+                                  "(own stream / KV cache / captured graphs each; profiles/r02_lm_lanes_ab.md)",
                            launches="decode steps replay captured CUDA graphs (8 steps x 62 kernels each); gpu_launches counts the eager launches "
                                     "(prefill, adapter) per generation"),
                e2e=dict(value=B_all * 283 / (ms_e2e * 1e-3), unit="tokens/s", ms_per_step=ms_e2e,
@@ -478,14 +480,9 @@ def bench_codec_strong(args, ctx, model, cfg, total):
                 note="last chunk of a shard that is not a multiple of the chunk size is computed in full and trimmed" if n_local % chunk else None)
 
 
-def bench_tokenize(args, ctx, model, cfg):
-    """HCodecTokenizer.tokenize-shaped leg (audio_tokenizer.py:68-74): raw 48 kHz waveform -> pad_wav -> Resample + HuBERT-base (mean of
-    13 hidden states, |x|^0.3) -> Codec.encode -> codes, everything on the device (SURVEY 8f.2 / 8f.3)."""
-    from unified_audio_b200 import ops
-    from unified_audio_b200.ssl import HCodecTokenizer, HUBERT_BASE, SSLFrontEnd
-    dev = ctx.dev
-    fe = SSLFrontEnd(HUBERT_BASE, in_rate=48000, compress=True).to(dev)
-    g = torch.Generator(device=dev).manual_seed(99)
+def init_ssl_(fe, dev, seed):
+    """random-init weights of an SSL front end (HuBERT-base / WavLM-base-plus architecture; no checkpoints offline)"""
+    g = torch.Generator(device=dev).manual_seed(seed)
     with torch.no_grad():
         for n, p in fe.named_parameters():
             if n.endswith("original0"):
@@ -499,6 +496,17 @@ def bench_tokenize(args, ctx, model, cfg):
         v = fe.encoder.pos_conv_embed.conv.parametrizations.weight.original1
         fe.encoder.pos_conv_embed.conv.parametrizations.weight.original0.copy_(v.pow(2).sum((0, 1), keepdim=True).sqrt() * 0.5)
     fe._w = None
+    return g
+
+
+def bench_tokenize(args, ctx, model, cfg):
+    """HCodecTokenizer.tokenize-shaped leg (audio_tokenizer.py:68-74): raw 48 kHz waveform -> pad_wav -> Resample + HuBERT-base (mean of
+    13 hidden states, |x|^0.3) -> Codec.encode -> codes, everything on the device (SURVEY 8f.2 / 8f.3)."""
+    from unified_audio_b200 import ops
+    from unified_audio_b200.ssl import HCodecTokenizer, HUBERT_BASE, SSLFrontEnd
+    dev = ctx.dev
+    fe = SSLFrontEnd(HUBERT_BASE, in_rate=48000, compress=True).to(dev)
+    g = init_ssl_(fe, dev, 99)
     tok = HCodecTokenizer(model, fe, cfg["sampling_rate"], cfg["encoder_config"]["target_frame_rate"])
     B = args.batch
     T = int(args.seconds * cfg["sampling_rate"]) - 700               # not a multiple of the hop: pad_wav has work to do
@@ -521,6 +529,62 @@ def bench_tokenize(args, ctx, model, cfg):
                 gpu_launches=int(launches),
                 roofline=dict(bound="tensor", achieved=tf, peak=peaks["tf_sus"] * ctx.world, unit="TFLOP/s", frac=tf / (peaks["tf_sus"] * ctx.world),
                               kernel="whole tokenize path, algorithmic FLOPs (SSL conv stack + 12 encoder layers + codec encoder / semantic encoder / RVQ)"))
+
+
+def bench_unise_sr(args, ctx, lm):
+    """BASELINE configs[2] as written - "UniSE SR: WavLM feats + AR-LM decode + codec decode, batch=32" - through the reference's
+    caller surface (unise.Model.enhance == the body of test_step, U/model/model.py:174-193): one utterance of 32 x 5 s @ 16 kHz per GPU ->
+    wrap-pad + segmenting -> WavLM-base-plus mean hidden state -> LLM_SFT.generate (greedy, 33 + 250 steps) -> BiCodec.detokenize ->
+    waveform, everything on the device.  The decoder is BiCodec, the codec UniSE actually feeds.  Stage split by CUDA events."""
+    from unified_audio_b200 import ops
+    from unified_audio_b200.bicodec import BICODEC_CONFIG, BiCodec
+    from unified_audio_b200.ssl import SSLFrontEnd, WAVLM_BASE_PLUS
+    from unified_audio_b200.unise import SEG_LEN, BiCodecTokenizer, Model
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    wavlm = SSLFrontEnd(WAVLM_BASE_PLUS, in_rate=16000, compress=False).to(dev)
+    init_ssl_(wavlm, dev, 98)
+    codec = BiCodec(BICODEC_CONFIG).to(dev)
+    init_bicodec_(codec, dev)
+    model = Model(None, tokenizer=BiCodecTokenizer(codec), dnn=lm, semantic_model=wavlm)
+    B = 32
+    T = B * SEG_LEN - 1234                                   # the last segment is wrap-padded
+    g = torch.Generator().manual_seed(3200 + rank)
+    src_h = (0.1 * torch.randn(1, T, generator=g)).pin_memory()
+    src = src_h.to(dev)
+    out_h = torch.empty(T).pin_memory()
+    for _ in range(2):
+        model.enhance("se", None, src)
+    steps = min(args.steps, 5)
+    ops.launch_count_reset()
+    ms = ctx.timed(lambda: model.enhance("se", None, src), steps)
+    launches = ops.launch_count() // steps
+
+    def e2e_step():
+        out_h.copy_(model.enhance("se", None, src_h.to(dev, non_blocking=True)), non_blocking=True)
+    ms_e2e = ctx.timed(e2e_step, steps)
+    # stage split (one more step, events between the stages)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    seg = model._segments(src)
+    seg = seg / src.abs().max(dim=-1, keepdim=True)[0]
+    feats = model.extract_semantic_features(seg)
+    ev[1].record()
+    gids, sids = lm.generate("se", None, None, model.mel_like(seg), feats, do_sample=False)
+    ev[2].record()
+    model._detok(gids, sids, T)
+    ev[3].record()
+    torch.cuda.synchronize()
+    split = dict(wavlm_ms=ev[0].elapsed_time(ev[1]), lm_generate_ms=ev[1].elapsed_time(ev[2]), bicodec_ms=ev[2].elapsed_time(ev[3]))
+    del model, codec, wavlm
+    return dict(metric="unise_sr_pipeline_samples_per_s", value=world * T / (ms * 1e-3), unit="samples/s (16 kHz)", n_gpus=world, steps=steps,
+                ms_per_step=ms, higher_is_better=True, scaling="weak", data="synthetic", tokens_per_s=world * B * 283 / (ms * 1e-3),
+                config=dict(workload=f"UniSE SR test_step: 1 utterance of {T} samples ({B} x 5 s segments) per GPU: wrap-pad -> WavLM-base-plus "
+                                     "features -> AR-LM greedy generate (252 prefix + 283 steps) -> BiCodec detokenize -> waveform",
+                            batch_per_gpu=B, precision="WavLM / LM / BiCodec: 3-term split (fp32-grade)"),
+                stage_split=split, gpu_launches=int(launches),
+                e2e=dict(value=world * T / (ms_e2e * 1e-3), unit="samples/s (16 kHz)", ms_per_step=ms_e2e, h2d_bytes_per_step=T * 4 * world,
+                         d2h_bytes_per_step=T * 4 * world))
 
 
 def bench_h15(args, ctx):
@@ -904,6 +968,33 @@ def bicodec_flops_per_clip(cfg, T):
     return f
 
 
+def init_bicodec_(m, dev):
+    """random-init weights of the BiCodec detokenize path (weight-norm gains ~ ||v||, residual branches damped, as oracle.bicodec.make_state_dict)"""
+    g = torch.Generator(device=dev).manual_seed(5)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith("alpha"):
+                p.copy_(1 + 0.3 * torch.rand(p.shape, generator=g, device=dev))
+            elif n.endswith(("weight_g",)):
+                p.fill_(1.0)
+            elif p.dim() >= 2:
+                fan = p[0].numel() if "block.1.weight_v" not in n else 2 * p.shape[0]
+                p.copy_(torch.randn(p.shape, generator=g, device=dev) / fan ** 0.5)
+            elif n.endswith(("gamma",)):
+                p.fill_(1.0 / 12)
+            elif n.endswith(("norm.weight", "scale.bias", "final_layer_norm.weight")):
+                p.fill_(1.0)
+            else:
+                p.copy_(0.02 * torch.randn(p.shape, generator=g, device=dev))
+        sdm = m.state_dict()
+        for n in list(sdm):
+            if n.endswith("weight_g"):
+                v = sdm[n[:-1] + "v"]
+                gain = 0.3 if ".block.3." in n else (0.1 if n.startswith("decoder.model.6.") else 1.0)
+                sdm[n].copy_(gain * v.reshape(v.shape[0], -1).norm(dim=1).reshape(sdm[n].shape))
+    m._w = None
+
+
 def run_bicodec(args):
     """Secondary line: BiCodec.detokenize, the decoder UniSE feeds its AR-LM tokens to (configs[2] back half):
     B=32 clips x 250 semantic tokens + 32 global tokens -> 5 s @ 16 kHz each."""
@@ -945,29 +1036,7 @@ def run_bicodec(args):
         dist.init_process_group("nccl", device_id=dev)
     cfg = BICODEC_CONFIG
     m = BiCodec(cfg).to(dev)
-    g = torch.Generator(device=dev).manual_seed(5)
-    with torch.no_grad():
-        for n, p in m.named_parameters():
-            if n.endswith("alpha"):
-                p.copy_(1 + 0.3 * torch.rand(p.shape, generator=g, device=dev))
-            elif n.endswith(("weight_g",)):
-                p.fill_(1.0)
-            elif p.dim() >= 2:
-                fan = p[0].numel() if "block.1.weight_v" not in n else 2 * p.shape[0]
-                p.copy_(torch.randn(p.shape, generator=g, device=dev) / fan ** 0.5)
-            elif n.endswith(("gamma",)):
-                p.fill_(1.0 / 12)
-            elif n.endswith(("norm.weight", "scale.bias", "final_layer_norm.weight")):
-                p.fill_(1.0)
-            else:
-                p.copy_(0.02 * torch.randn(p.shape, generator=g, device=dev))
-        sdm = m.state_dict()
-        for n in list(sdm):     # weight-norm gains ~ ||v||, residual branches damped (as oracle.bicodec.make_state_dict)
-            if n.endswith("weight_g"):
-                v = sdm[n[:-1] + "v"]
-                gain = 0.3 if ".block.3." in n else (0.1 if n.startswith("decoder.model.6.") else 1.0)
-                sdm[n].copy_(gain * v.reshape(v.shape[0], -1).norm(dim=1).reshape(sdm[n].shape))
-    m._w = None
+    init_bicodec_(m, dev)
     gt = torch.Generator().manual_seed(50 + rank)
     sem_h = torch.randint(0, cfg["quantizer"]["codebook_size"], (B, T), generator=gt).pin_memory()
     glob_h = torch.randint(0, 4096, (B, 1, 32), generator=gt).pin_memory()
@@ -1104,6 +1173,7 @@ def main():
         # the batch-256 sweep (configs[4]), the teacher-forced forward, the adaptive codec
         m = lm_box["m"]
         for name, fn in (("lm_sr_b256_strong", lambda: bench_lm_generate(args, ctx, m, "se", None, total_batch=256, steps=2)),
+                         ("unise_sr_pipeline", lambda: bench_unise_sr(args, ctx, m)),
                          ("lm_forward", lambda: bench_lm_forward(args, ctx, m)),
                          ("hcodec15_adaptive", lambda: bench_h15(args, ctx))):
             run_leg(ctx, sec, name, fn)

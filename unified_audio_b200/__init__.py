@@ -10,6 +10,8 @@ Public surface mirrors the reference (alibaba/unified-audio):
   SSLFrontEnd      <- HuBERT-base / WavLM-base-plus feature extraction as HCodecTokenizer.extract_ssl_features
                       (HCodec-2.0/audio_tokenizer.py:47-61) and Model.extract_semantic_features (U/model/model.py:38-51) drive them
   HCodecTokenizer  <- QuarkAudio-HCodec/HCodec-2.0/audio_tokenizer.py:21-79 (pad_wav / tokenize / detokenize)
+  unise.Model      <- QuarkAudio-UniSE/model/model.py:20-286 (extract_semantic_features / test_step: 'se', 'tse', 'ss') with
+                      unise.BiCodecTokenizer <- model/bicodec/audio_tokenizer.py:30-125 (detokenize)
 Kernels live in csrc/ behind the C ABI of include/quark_b200.h (lib/libquark_b200.so).
 """
 __version__ = "0.1.0"
@@ -22,3 +24,4 @@ from .llm import LLM_SFT  # noqa: E402,F401
 from .bicodec import BiCodec  # noqa: E402,F401
 from . import adaptive  # noqa: E402,F401
 from .ssl import HCodecTokenizer, HUBERT_BASE, SSLFrontEnd, WAVLM_BASE_PLUS, pad_wav, wrap_segments  # noqa: E402,F401
+from . import unise  # noqa: E402,F401

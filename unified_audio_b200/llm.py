@@ -111,7 +111,9 @@ class LLM_SFT(nn.Module):
         # generate() walks a batch in chunks of <= `chunk` sequences; `lanes` > 1 runs that many chunks CONCURRENTLY, each on its own
         # CUDA stream with its own KV cache / workspace / captured graphs (the decode step is a chain of ~62 short dependent kernels:
         # one chain leaves most of the GPU idle, independent chains fill it).  Tokens do not depend on either setting.
-        self.lanes = max(1, int(os.environ.get("QB_LM_LANES", "1")))
+        # Measured on B200 (profiles/r02_lm_lanes_ab.md), 256 sequences: 851.7 ms serial, 584.9 / 513.5 / 511.0 ms with 2 / 4 / 8 lanes;
+        # cutting a batch of <= 32 into smaller chunks is slower (a chain costs the same for 8, 16 or 32 rows), hence chunk = 32.
+        self.lanes = max(1, int(os.environ.get("QB_LM_LANES", "4")))
         self.chunk = min(32, max(1, int(os.environ.get("QB_LM_CHUNK", "32"))))
         self._lane_views = None
         self.eval()
