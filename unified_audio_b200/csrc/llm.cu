@@ -799,8 +799,10 @@ __global__ void lm_pack_weight_kernel(const float* __restrict__ w, long long tot
   out[i] = o;
 }
 
+// 256-thread variants are capped at 128 registers so that TWO CTAs fit an SM: the gate/up projection (inter/8 = 256 CTAs) and the
+// head (256 / 512 CTAs) then run in one / two waves on 148 SMs instead of two / four (QB_LM_SKINNY_OCC, measured in profiles/).
 template <int MODE, int SPW, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1)
 lm_skinny_kernel(const SkParams p) {
   constexpr int NT = MODE == SK_RESID ? 1 : 2;       // 8-column tiles per CTA
   __shared__ __align__(16) float red[NW][NT][32][8];
@@ -1139,11 +1141,18 @@ extern "C" int qb_lm_head_argmax(const float* x, int64_t B, int32_t hidden, cons
 }
 
 // ------------------------------------------------------------------------------------------ tensor-core decode (product path)
+// "Early" programmatic launch (griddepcontrol.launch_dependents BEFORE the kernel's own dependency wait) lets a whole cascade of
+// dependents become resident while older kernels still run.  Measured: 102.5 vs 103.9 ms per generate - and NOT token-stable once
+// several decode chains share the GPU: a dependent's L1 is invalidated when it is launched, a co-resident older kernel that still
+// reads x (every gate/up CTA reads all of x) re-fills the SM's L1 with the old lines, and the dependent then reads them after its
+// wait.  With the trigger after the main loop (the product setting) a dependent is launched only when every older kernel's loads
+// of mutable data are over.  The switch therefore needs QB_LM_UNSAFE=1 next to QB_LM_PDL_EARLY=1 (experiments only).
 static int lm_pdl_early() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("QB_LM_PDL_EARLY");
-    v = (e && e[0] == '1') ? 1 : 0;
+    const char* u = getenv("QB_LM_UNSAFE");
+    v = (e && e[0] == '1' && u && u[0] == '1') ? 1 : 0;
   }
   return v;
 }
