@@ -978,6 +978,7 @@ lm_skinny_kernel(const SkParams p) {
 // one CTA per (head, batch row), 16 half-warps each walking keys hw, hw+16, ... with an online softmax; a key row
 // (64 fp32) is one coalesced 256-byte read by 16 lanes, K and V of 4 keys in flight per lane; the 16 partial
 // (max, sum, acc) triples are merged through shared memory in a fixed order.  No score buffer: any cache length.
+template <int LM_ATT_U>
 __global__ void __launch_bounds__(256)
 lm_decode_attn2_kernel(const float* __restrict__ q, const float* __restrict__ kc, const float* __restrict__ vc, int H,
                        int Lmax, const int* __restrict__ posp, float* __restrict__ out, int pdl_early) {
@@ -993,19 +994,19 @@ lm_decode_attn2_kernel(const float* __restrict__ q, const float* __restrict__ kc
   const float4* vb = reinterpret_cast<const float4*>(vc + ((size_t)b * H + h) * Lmax * 64) + c;
   float m = -INFINITY, l = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int base = warp * 2; base < n; base += 64) {       // warp-uniform trip count (full-mask shuffles inside)
+  for (int base = warp * 2; base < n; base += 16 * LM_ATT_U) {       // warp-uniform trip count (full-mask shuffles inside)
     const int j0 = base + (lane >> 4);
-    float4 kv[4], vv[4];
-    float s[4];
+    float4 kv[LM_ATT_U], vv[LM_ATT_U];
+    float s[LM_ATT_U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < LM_ATT_U; ++u) {
       const int j = j0 + 16 * u;
       const bool ok = j < n;
       kv[u] = ok ? kb[(size_t)j * 16] : make_float4(0.f, 0.f, 0.f, 0.f);
       vv[u] = ok ? vb[(size_t)j * 16] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < LM_ATT_U; ++u) {
       float d = fmaf(qv.x, kv[u].x, fmaf(qv.y, kv[u].y, fmaf(qv.z, kv[u].z, qv.w * kv[u].w)));
       d += __shfl_xor_sync(0xffffffffu, d, 8);
       d += __shfl_xor_sync(0xffffffffu, d, 4);
@@ -1013,13 +1014,15 @@ lm_decode_attn2_kernel(const float* __restrict__ q, const float* __restrict__ kc
       d += __shfl_xor_sync(0xffffffffu, d, 1);
       s[u] = (j0 + 16 * u < n) ? d : -INFINITY;
     }
-    const float mn = fmaxf(fmaxf(m, fmaxf(s[0], s[1])), fmaxf(s[2], s[3]));
+    float mn = m;
+#pragma unroll
+    for (int u = 0; u < LM_ATT_U; ++u) mn = fmaxf(mn, s[u]);
     if (mn > -INFINITY) {                       // (the odd half-warp can run out of keys one trip early)
       const float corr = expf(m - mn);
       l *= corr;
       acc.x *= corr; acc.y *= corr; acc.z *= corr; acc.w *= corr;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < LM_ATT_U; ++u) {
         const float pr = expf(s[u] - mn);
         l += pr;
         acc.x = fmaf(pr, vv[u].x, acc.x); acc.y = fmaf(pr, vv[u].y, acc.y);
@@ -1211,7 +1214,11 @@ extern "C" int qb_lm_decode_layer_tc(float* x, int64_t B, int32_t hidden, int32_
   // RMSNorm + QKV + RoPE + cache append
   p.x = x; p.K = hidden; p.W = (const uint4*)wqkv; p.out = q_buf;
   if (int e = launch_skinny<SK_QKV>(p, 3 * heads * 4, st)) return e;
-  QB_CHECK_CUDA(launch_pdl(lm_decode_attn2_kernel, dim3((unsigned)heads, (unsigned)B), dim3(256), 0, st, (const float*)q_buf,
+  // keys in flight per half-warp trip (K and V rows of LM_ATT_U keys per lane): QB_LM_ATT_U = 4 | 8, default LM_ATT_U_DEFAULT (common.cuh)
+  static int att_u = -1;
+  if (att_u < 0) { const char* e = getenv("QB_LM_ATT_U"); att_u = e ? atoi(e) : LM_ATT_U_DEFAULT; }
+  auto att = att_u == 8 ? lm_decode_attn2_kernel<8> : lm_decode_attn2_kernel<4>;
+  QB_CHECK_CUDA(launch_pdl(att, dim3((unsigned)heads, (unsigned)B), dim3(256), 0, st, (const float*)q_buf,
                            (const float*)k_cache, (const float*)v_cache, (int)heads, (int)Lmax, (const int*)pos, attn_buf,
                            lm_pdl_early()));
   // o_proj + residual

@@ -27,6 +27,7 @@
 namespace qb {
 extern std::atomic<long long> g_launches;
 
+constexpr int LM_ATT_U = LM_ATT_U_DEFAULT;      // same key grouping as lm_decode_attn2_kernel: bit-identical tokens
 constexpr int ST_MAX_LAYERS = 16, ST_THREADS = 512, ST_WSMEM = 4608;       // floats of shared memory per 256-thread worker
 
 struct StepLayer {
@@ -277,19 +278,19 @@ __device__ __forceinline__ void attn_item(const float* __restrict__ q, const flo
   const float4* vb = reinterpret_cast<const float4*>(vc + ((size_t)b * H + h) * Lmax * 64) + c;
   float m = -INFINITY, l = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int base = warp * 2; base < n; base += 64) {
+  for (int base = warp * 2; base < n; base += 16 * LM_ATT_U) {
     const int j0 = base + (lane >> 4);
-    float4 kv[4], vv[4];
-    float s[4];
+    float4 kv[LM_ATT_U], vv[LM_ATT_U];
+    float s[LM_ATT_U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < LM_ATT_U; ++u) {
       const int j = j0 + 16 * u;
       const bool ok = j < n;
       kv[u] = ok ? __ldcg(kb + (size_t)j * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
       vv[u] = ok ? __ldcg(vb + (size_t)j * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < LM_ATT_U; ++u) {
       float d = fmaf(qv.x, kv[u].x, fmaf(qv.y, kv[u].y, fmaf(qv.z, kv[u].z, qv.w * kv[u].w)));
       d += __shfl_xor_sync(0xffffffffu, d, 8);
       d += __shfl_xor_sync(0xffffffffu, d, 4);
@@ -297,13 +298,15 @@ __device__ __forceinline__ void attn_item(const float* __restrict__ q, const flo
       d += __shfl_xor_sync(0xffffffffu, d, 1);
       s[u] = (j0 + 16 * u < n) ? d : -INFINITY;
     }
-    const float mn = fmaxf(fmaxf(m, fmaxf(s[0], s[1])), fmaxf(s[2], s[3]));
+    float mn = m;
+#pragma unroll
+    for (int u = 0; u < LM_ATT_U; ++u) mn = fmaxf(mn, s[u]);
     if (mn > -INFINITY) {
       const float corr = expf(m - mn);
       l *= corr;
       acc.x *= corr; acc.y *= corr; acc.z *= corr; acc.w *= corr;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < LM_ATT_U; ++u) {
         const float pr = expf(s[u] - mn);
         l += pr;
         acc.x = fmaf(pr, vv[u].x, acc.x); acc.y = fmaf(pr, vv[u].y, acc.y);
