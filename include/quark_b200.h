@@ -287,6 +287,11 @@ int qb_lm_decode_layer_tc(float* x, int64_t B, int32_t hidden, int32_t heads, in
                           const qb_half* wo, const qb_half* wgate, const qb_half* wup, const qb_half* wdown,
                           float* k_cache, float* v_cache, int32_t Lmax, const int32_t* pos, const float* rope_cos,
                           const float* rope_sin, float* q_buf, float* attn_buf, float* mlp_buf, void* stream);
+/* Keys whose K / V rows one lane of the cached-decode attention keeps in flight per trip: 8 (default; a single decode chain is
+ * latency-bound) or 4 (several chains sharing the GPU are throughput-bound - LLM_SFT.generate's lanes select it).  Process-wide;
+ * read at launch (and therefore fixed inside a captured graph).  Tokens do not depend on it only up to the fp32 summation order of
+ * the online softmax: set it once per decode state. */
+int qb_lm_set_att_unroll(int32_t keys_per_lane);
 /* as qb_lm_head_argmax with a packed head; max_cols and the range width must be multiples of 16;
  * part_val/part_idx: scratch [max_cols/16 * 32]. */
 int qb_lm_head_argmax_tc(const float* x, int64_t B, int32_t hidden, const qb_half* w_head, const int32_t* range,

@@ -244,6 +244,7 @@ def test_lm_generate_lanes_identical(lib, task):
     B, T = 7, 6
     mix = torch.randn(B, T, cfg["feats_dim"], generator=g).cuda()
     enr = torch.randn(B, T, cfg["feats_dim"], generator=g).cuda() if task == "tse" else None
+    m.lane_att_unroll = m.att_unroll          # same fp32 summation order of the decode attention on every lane: bit-equal tokens
     m.chunk, m.lanes = 2, 1
     ref_g = m.generate(task, enr, enr, mix, mix, do_sample=False)
     ref_s = m.generate(task, enr, enr, mix, mix, do_sample=True, seed=77)

@@ -102,6 +102,7 @@ SIGNATURES = {
     "qb_lm_pack_weight": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
     "qb_lm_decode_layer_tc": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp]),
+    "qb_lm_set_att_unroll": (C.c_int, [_i32]),
     "qb_lm_head_argmax_tc": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "qb_ssl_conv0_workspace_bytes": (C.c_int64, [_i64, _i64, _i32]),
     "qb_ssl_conv0_gn_gelu": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),

@@ -51,7 +51,7 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __ex
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 // cached-decode attention: keys whose K / V rows one lane keeps in flight per trip (llm.cu lm_decode_attn2_kernel, llm_step.cu attn_item)
 #ifndef LM_ATT_U_DEFAULT
-#define LM_ATT_U_DEFAULT 4
+#define LM_ATT_U_DEFAULT 8
 #endif
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }

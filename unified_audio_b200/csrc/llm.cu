@@ -1201,6 +1201,13 @@ extern "C" int qb_lm_pack_weight(const float* w, int64_t n, int64_t k, qb_half* 
   return 0;
 }
 
+static int g_lm_att_unroll = LM_ATT_U_DEFAULT;
+extern "C" int qb_lm_set_att_unroll(int32_t keys_per_lane) {
+  QB_REQUIRE(keys_per_lane == 4 || keys_per_lane == 8, "lm_set_att_unroll: 4 or 8 (got %d)", (int)keys_per_lane);
+  g_lm_att_unroll = keys_per_lane;
+  return 0;
+}
+
 extern "C" int qb_lm_decode_layer_tc(float* x, int64_t B, int32_t hidden, int32_t heads, int32_t inter, const qb_half* wqkv,
                                      const qb_half* wo, const qb_half* wgate, const qb_half* wup, const qb_half* wdown,
                                      float* k_cache, float* v_cache, int32_t Lmax, const int32_t* pos, const float* rope_cos,
@@ -1214,10 +1221,10 @@ extern "C" int qb_lm_decode_layer_tc(float* x, int64_t B, int32_t hidden, int32_
   // RMSNorm + QKV + RoPE + cache append
   p.x = x; p.K = hidden; p.W = (const uint4*)wqkv; p.out = q_buf;
   if (int e = launch_skinny<SK_QKV>(p, 3 * heads * 4, st)) return e;
-  // keys in flight per half-warp trip (K and V rows of LM_ATT_U keys per lane): QB_LM_ATT_U = 4 | 8, default LM_ATT_U_DEFAULT (common.cuh)
-  static int att_u = -1;
-  if (att_u < 0) { const char* e = getenv("QB_LM_ATT_U"); att_u = e ? atoi(e) : LM_ATT_U_DEFAULT; }
-  auto att = att_u == 8 ? lm_decode_attn2_kernel<8> : lm_decode_attn2_kernel<4>;
+  // keys in flight per half-warp trip (K and V rows of LM_ATT_U keys per lane), qb_lm_set_att_unroll: 8 for a single decode chain
+  // (latency-bound: 103.3 -> 98.2 ms per SR generate, 111.5 -> 101.9 ms TSE), 4 when several chains share the GPU (throughput-
+  // bound: 474 vs 492 ms for 256 sequences on 4 lanes) - profiles/r02_lm_lanes_ab.md
+  auto att = g_lm_att_unroll == 4 ? lm_decode_attn2_kernel<4> : lm_decode_attn2_kernel<8>;
   QB_CHECK_CUDA(launch_pdl(att, dim3((unsigned)heads, (unsigned)B), dim3(256), 0, st, (const float*)q_buf,
                            (const float*)k_cache, (const float*)v_cache, (int)heads, (int)Lmax, (const int*)pos, attn_buf,
                            lm_pdl_early()));

@@ -114,6 +114,10 @@ class LLM_SFT(nn.Module):
         # Measured on B200 (profiles/r02_lm_lanes_ab.md), 256 sequences: 851.7 ms serial, 584.9 / 513.5 / 511.0 ms with 2 / 4 / 8 lanes;
         # cutting a batch of <= 32 into smaller chunks is slower (a chain costs the same for 8, 16 or 32 rows), hence chunk = 32.
         self.lanes = max(1, int(os.environ.get("QB_LM_LANES", "4")))
+        # K / V rows a lane of the decode attention keeps in flight: 8 for one chain (latency-bound), 4 on concurrent lanes
+        # (throughput-bound); QB_LM_ATT_U pins it.  Fixed per decode state (it is baked into the captured graphs).
+        self.att_unroll = int(os.environ.get("QB_LM_ATT_U", "8"))
+        self.lane_att_unroll = int(os.environ.get("QB_LM_ATT_U", "4"))
         self.chunk = min(32, max(1, int(os.environ.get("QB_LM_CHUNK", "32"))))
         self._lane_views = None
         self.eval()
@@ -244,6 +248,8 @@ class LLM_SFT(nn.Module):
 
     def _decode_layers(self, x: torch.Tensor, B: int, cache: StaticKVCache):
         W = self._prepare()
+        if self.decode_kernel == "tc":
+            ops.lm_set_att_unroll(self.att_unroll)
         H, heads, inter = self.hidden, self.heads, 4 * self.hidden
         qb, ab, mb = self._buf("dq", (B, H)), self._buf("da", (B, H)), self._buf("dm", (B, inter))
         layer = ops.lm_decode_layer_tc if self.decode_kernel == "tc" else ops.lm_decode_layer
@@ -414,6 +420,7 @@ class LLM_SFT(nn.Module):
             v = copy.copy(self)
             v._ws, v._gen_state, v._lane_views = {}, {}, None
             v.lanes = 1
+            v.att_unroll = self.lane_att_unroll
             lanes.append((v, torch.cuda.Stream(device=self._dev())))
         return lanes
 

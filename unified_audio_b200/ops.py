@@ -303,6 +303,10 @@ def lm_pack_weight(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def lm_set_att_unroll(keys_per_lane: int):
+    _lib.check(_lib.load().qb_lm_set_att_unroll(int(keys_per_lane)))
+
+
 def lm_decode_layer_tc(x, B, hidden, heads, inter, L, kc, vc, Lmax, pos, cos, sin, q_buf, attn_buf, mlp_buf):
     _lib.check(_lib.load().qb_lm_decode_layer_tc(_p(x), B, hidden, heads, inter, _p(L["wqkv_p"]), _p(L["wo_p"]), _p(L["wg_p"]),
                                                  _p(L["wu_p"]), _p(L["wd_p"]), _p(kc), _p(vc), Lmax, _p(pos), _p(cos), _p(sin),
