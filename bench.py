@@ -639,9 +639,13 @@ def bench_h15(args, ctx):
     _, lens = adaptive.extract_lengths(out["acoustic_codes"], model.codebook_size)
     n_tok = (lens > 0).sum(1).float()
     step()
+    step()
     ops.launch_count_reset()
-    ms = ctx.timed(step, max(2, min(args.steps, 3)))
-    launches = ops.launch_count() // max(2, min(args.steps, 3))
+    k15 = max(2, min(args.steps, 3))
+    ms_a = ctx.timed(step, k15)
+    launches = ops.launch_count() // k15
+    ms_b = ctx.timed(step, k15)                 # ~960 eager launches + two host reads per step: the first timed pass still grows the allocator
+    ms = min(ms_a, ms_b)
     peaks = load_peaks()
     tf = ctx.world * flops[0] / (ms * 1e-3) / 1e12
     n_samples = B * T50 * 320
@@ -703,7 +707,7 @@ def bench_h15(args, ctx):
     torch.cuda.empty_cache()
     return dict(e2e=dict(value=ctx.world * n_samples / (ms_e2e * 1e-3), unit=UNIT, ms_per_step=ms_e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h), **extra,
                 metric="hcodec15_adaptive_encode_decode_samples_per_s", value=ctx.world * n_samples / (ms * 1e-3), unit=UNIT, ms_per_step=ms,
-                n_gpus=ctx.world, scaling="weak",
+                timed_passes_ms=[ms_a, ms_b], n_gpus=ctx.world, scaling="weak",
                 config=dict(workload=f"HCodec-1.5 adaptive (config_adaptive_v3) batch={B} x {T50 / 50:g} s @16 kHz encode + decode, threshold 0.6",
                             batch_per_gpu=B, frames_25hz=T50 // 2, tokens_per_clip_mean=float(n_tok.mean()), tokens_per_clip_max=int(n_tok.max()),
                             precision_policy=args.precision, launch="kernel by kernel (data-dependent sequence lengths)"),
