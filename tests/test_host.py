@@ -323,3 +323,39 @@ def test_oracle_adaptive_alignment_matches_reference_fixture():
         assert torch.equal(plain, codes) and torch.equal(l2, lens.clamp(min=1))
         grouped = torch.randn(h.shape[0], 5, a.shape[1]) * (lens > 0)[:, None]
         assert torch.equal(oa.deaggregate(grouped, a)[:, :, : int(lens[0].sum())][0], oa.deaggregate_by_lengths(grouped, lens)[0])
+
+
+def test_unise_face_host_logic():
+    """unise.Model without a GPU: the checkpoint surface (state_dict holds the LM only, under `dnn.`, like model.py:81-91), the
+    shape-only mel against the reference's formula (model.py:53-79 evaluated here with torch.stft on the CPU), the segment count of
+    the wrap-pad rule, and the refusal to run off the GPU (no fallback)."""
+    import math
+    from oracle import bicodec as ob
+    from oracle import llama
+    from unified_audio_b200.bicodec import BiCodec
+    from unified_audio_b200.llm import LLM_SFT
+    from unified_audio_b200.ssl import SSLFrontEnd
+    from unified_audio_b200.unise import SEG_LEN, BiCodecTokenizer, Model
+    c = dict(conv_dim=[64] * 7, conv_kernel=[10, 3, 3, 3, 3, 2, 2], conv_stride=[5, 2, 2, 2, 2, 2, 2], hidden=128, layers=2, heads=2,
+             ffn=256, pos_k=16, pos_groups=4, eps=1e-5, num_buckets=32, max_distance=80, kind="wavlm")
+    lcfg = llama.lm_small(hidden=128, layers=2, heads=2, gsize=4096, ssize=256, feats=128)
+    lm = LLM_SFT(num_tasks=lcfg["num_tasks"], task_map=lcfg["task_map"], feats_dim=lcfg["feats_dim"], llm_base_config=lcfg["llm_base_config"])
+    lsd = llama.make_lm_state_dict(lcfg, 3, 2.0)
+    lm.load_state_dict(lsd, strict=True)
+    model = Model(None, tokenizer=BiCodecTokenizer(BiCodec(ob.bicodec_small())), dnn=lm, semantic_model=SSLFrontEnd(c, in_rate=16000))
+    keys = set(model.state_dict().keys())
+    assert keys == {"dnn." + k for k in lm.state_dict().keys()}
+    ckpt = {"dnn." + k: v + 1.0 if v.is_floating_point() else v for k, v in lsd.items()}
+    ckpt["tokenizer.model.whatever"] = torch.zeros(1)            # excluded sub-modules of a Lightning checkpoint are ignored
+    model.load_state_dict(ckpt)
+    k0 = next(iter(lsd))
+    assert torch.equal(model.dnn.state_dict()[k0], lsd[k0] + 1.0)
+    x = 0.1 * torch.randn(2, 48000 - 77, generator=torch.Generator().manual_seed(4))
+    mel = model.stft_logmel(x)
+    assert model.mel_like(x).shape == mel.shape == (2, math.ceil((48000 - 77) / 320), 80) and bool(torch.isfinite(mel).all())
+    assert model.mel_frames(SEG_LEN) == 250                       # = the LM's semantic_length for a 5 s segment (llm_sft.py:166)
+    assert model.forward(None) is None                            # model.py:93-94
+    with pytest.raises(RuntimeError):
+        model.enhance("se", None, x[:1])
+    with pytest.raises(NotImplementedError):
+        model.tokenizer.tokenize(x)
