@@ -359,3 +359,33 @@ def test_unise_face_host_logic():
         model.enhance("se", None, x[:1])
     with pytest.raises(NotImplementedError):
         model.tokenizer.tokenize(x)
+
+
+def test_unise_test_step_control_flow_matches_reference_fixture(monkeypatch):
+    """tests/golden/unise_glue.npz holds what the REFERENCE'S OWN `Model.test_step` (U/model/model.py:170-286, imported and run
+    unmodified by oracle/make_golden_unise.py) hands to its wav writer when its four components are the deterministic stand-ins of
+    oracle/unise_stubs.py.  `unise.Model._enhance` with the same stand-ins must produce the same waveforms bit for bit: wrap-pad,
+    segmenting, 'se' normalisation, enrollment repetition, the se -> tse -> rtse chain of 'ss', trimming, and the sequence of
+    generate() calls.  (CPU: the device kernel behind wrap_segments is replaced by the NumPy expression it implements - its own
+    parity is tests/test_ssl_gpu.py::test_tokenizer_glue_and_end_to_end.)"""
+    import math
+    from oracle import unise_stubs as st
+    from oracle.make_golden_unise import digest, make_cases
+    from unified_audio_b200 import unise
+
+    def wrap_np(src, seg_len):
+        pad = math.ceil(src.shape[-1] / seg_len) * seg_len - src.shape[-1]
+        return torch.from_numpy(np.pad(src.numpy(), [(0, 0), (0, pad)], "wrap")).reshape(-1, seg_len)
+    monkeypatch.setattr(unise, "wrap_segments", wrap_np)
+    z = np.load(os.path.join(GOLD, "unise_glue.npz"))
+    model = unise.Model(None, tokenizer=st.Tokenizer(), dnn=st.Dnn(), semantic_model=st.SemanticModel())
+    for name, (enroll, src) in make_cases().items():
+        mode = name.split("_")[0]
+        model.dnn.calls = []
+        with torch.no_grad():
+            out = model._enhance(mode, enroll, src)
+        outs = out if isinstance(out, tuple) else (out,)
+        assert model.dnn.calls == json.loads(str(z[f"{name}.calls"])), name
+        for i, o in enumerate(outs):
+            got, want = digest(o.numpy()), z[f"{name}.est{i}"]
+            assert got.shape == want.shape and np.array_equal(got, want), f"{name} output {i} differs from the reference's test_step"
