@@ -389,3 +389,31 @@ def test_unise_test_step_control_flow_matches_reference_fixture(monkeypatch):
         for i, o in enumerate(outs):
             got, want = digest(o.numpy()), z[f"{name}.est{i}"]
             assert got.shape == want.shape and np.array_equal(got, want), f"{name} output {i} differs from the reference's test_step"
+
+
+def test_oracle_lm_control_flow_matches_reference_fixture():
+    """tests/golden/lm_reference.npz holds outputs of the REFERENCE'S OWN `LLM_SFT` (U/model/llm/llm_sft.py, llm.py: unmodified
+    `__init__`, conditioning prefix, teacher-forced `forward`, `loss_function`, both decoding loops of `generate`, `sample_logits`;
+    only `llm_forward` is bound to this image's transformers - oracle/make_golden_lm_reference.py).  The oracle must reproduce them:
+    loss and accuracy of the teacher-forced pass, every greedy token for 'se' / 'tse' / 'rtse', the filtered support of sample_logits."""
+    from oracle import llama
+    z = np.load(os.path.join(GOLD, "lm_reference.npz"))
+    meta = json.loads(str(z["meta"]))
+    cfg = meta["cfg"]
+    sd = llama.make_lm_state_dict(cfg, meta["seed"], meta["gain"])
+    mix, enr = torch.from_numpy(z["mix"]), torch.from_numpy(z["enroll"])
+    gids, sids = torch.from_numpy(z["gids"]), torch.from_numpy(z["sids"])
+    for task in ("se", "tse", "rtse"):
+        e = None if task == "se" else enr
+        loss, acc = llama.sft_forward(sd, cfg, task, e, mix, gids, sids)
+        assert abs(float(loss) - float(z[f"{task}.loss"])) < 1e-5 * abs(float(z[f"{task}.loss"])) and float(acc) == float(z[f"{task}.acc"])
+        gg, ss = llama.sft_generate(sd, cfg, task, e, mix, meta["T"])
+        assert np.array_equal(gg.numpy(), z[f"{task}.gen_global"]) and np.array_equal(ss.numpy(), z[f"{task}.gen_semantic"]), task
+    lg = torch.from_numpy(z["sample.logits"])
+    for top_k, top_p, temp in ((50, 0.95, 0.8), (5, 0.5, 1.0), (20, 1.0, 0.3)):
+        probs = llama.sample_filter(lg.clone(), temperature=temp, top_k=top_k, top_p=top_p)
+        sup = np.unpackbits(z[f"sample.k{top_k}.p{top_p}.t{temp}.support"], axis=1)[:, :lg.shape[1]].astype(bool)
+        assert np.array_equal((probs > 0).numpy(), sup)
+        assert np.allclose(probs.max(-1).values.numpy(), z[f"sample.k{top_k}.p{top_p}.t{temp}.probs_max"], rtol=1e-5, atol=1e-7)
+    rep = json.load(open(os.path.join(GOLD, "lm_reference_pinning_report.json")))
+    assert all(rep[t]["tokens_identical"] for t in ("se", "tse", "rtse", "full_config_tse"))
