@@ -417,3 +417,29 @@ def test_oracle_lm_control_flow_matches_reference_fixture():
         assert np.allclose(probs.max(-1).values.numpy(), z[f"sample.k{top_k}.p{top_p}.t{temp}.probs_max"], rtol=1e-5, atol=1e-7)
     rep = json.load(open(os.path.join(GOLD, "lm_reference_pinning_report.json")))
     assert all(rep[t]["tokens_identical"] for t in ("se", "tse", "rtse", "full_config_tse"))
+
+
+def test_oracle_tokenizer_chain_matches_reference_fixture():
+    """tests/golden/tokenizer_small.npz = outputs of the REFERENCE'S OWN `HCodecTokenizer` (H2/audio_tokenizer.py:47-79: unmodified
+    pad_wav / extract_ssl_features / tokenize / detokenize over the reference's `vq.Codec`, transformers' HubertModel and torchaudio's
+    Resample - oracle/make_golden_tokenizer.py).  The oracle chain must reproduce them: same padding, features (away from the
+    compression's singular point at 0), identical acoustic and semantic codes, the same reconstruction."""
+    from oracle import hcodec2
+    from oracle import hubert as oh
+    from oracle import weights
+    z = np.load(os.path.join(GOLD, "tokenizer_small.npz"))
+    meta = json.loads(str(z["meta"]))
+    c, cfg = meta["hubert"], meta["codec_cfg"]
+    sd = weights.make_h2_state_dict(cfg, meta["seed_codec"])
+    fsd = oh.make_state_dict(c, meta["seed_ssl"])
+    wav = torch.from_numpy(z["wav"])
+    hop = 3840
+    padded = torch.nn.functional.pad(wav, (0, -(-wav.shape[-1] // hop) * hop - wav.shape[-1]))       # audio_tokenizer.py:63-66
+    feats = oh.extract_ssl_features(fsd, c, padded)
+    fr = torch.from_numpy(z["feats"])
+    big = fr.abs() > 0.2 * fr.abs().max()
+    assert feats.shape == fr.shape and float((feats - fr).abs()[big].max() / fr.abs().max()) < 1e-4
+    ac, sc = hcodec2.codec_encode(sd, cfg, padded, feats.transpose(1, 2))
+    assert np.array_equal(ac.numpy(), z["acoustic"]) and np.array_equal(sc.numpy(), z["semantic"])
+    rec = hcodec2.codec_decode(sd, cfg, ac, sc)
+    assert rec.shape == z["rec"].shape and float((rec - torch.from_numpy(z["rec"])).abs().max() / np.abs(z["rec"]).max()) < 1e-5
