@@ -94,6 +94,11 @@ def main():
             out[f"{name}.est{i}"] = digest(data)
         out[f"{name}.calls"] = np.array(json.dumps(m.dnn.calls))
         print(name, "reference test_step ->", [(os.path.basename(p), d.shape) for p, d, _ in written], "generate calls:", m.dnn.calls)
+    # ---- stft_logmel (model.py:53-79), unmodified: dead compute for the LM (only its length is read) but part of the surface
+    xm = 0.1 * torch.randn(2, 16000 - 77, generator=torch.Generator().manual_seed(21))
+    mel = m.stft_logmel(xm)
+    out["mel.y"] = mel.numpy()                       # the input is re-made from its seed (21) by the test
+    print("stft_logmel", tuple(mel.shape))
     meta = dict(reference="QuarkAudio-UniSE/model/model.py:170-286 (unmodified test_step, stub components oracle/unise_stubs.py)",
                 cases=list(cases))
     path = os.path.join(ROOT, "tests", "golden", "unise_glue.npz")

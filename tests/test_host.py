@@ -389,6 +389,10 @@ def test_unise_test_step_control_flow_matches_reference_fixture(monkeypatch):
         for i, o in enumerate(outs):
             got, want = digest(o.numpy()), z[f"{name}.est{i}"]
             assert got.shape == want.shape and np.array_equal(got, want), f"{name} output {i} differs from the reference's test_step"
+    xm = 0.1 * torch.randn(2, 16000 - 77, generator=torch.Generator().manual_seed(21))
+    mel = model.stft_logmel(xm)                                          # vs the reference's own stft_logmel on the same input (model.py:53-79)
+    assert mel.shape == z["mel.y"].shape == model.mel_like(xm).shape
+    assert float((mel - torch.from_numpy(z["mel.y"])).abs().max()) < 1e-4
 
 
 def test_oracle_lm_control_flow_matches_reference_fixture():
