@@ -215,7 +215,8 @@ def run_leg(ctx, sec, name, fn):
         sec[name] = fn()
     except Exception as e:
         sec[name] = dict(error=repr(e))
-        torch.cuda.synchronize()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
     if isinstance(sec[name], dict):
         sec[name]["leg_wall_s"] = round(time.perf_counter() - t0, 1)
 

@@ -447,3 +447,32 @@ def test_oracle_tokenizer_chain_matches_reference_fixture():
     assert np.array_equal(ac.numpy(), z["acoustic"]) and np.array_equal(sc.numpy(), z["semantic"])
     rec = hcodec2.codec_decode(sd, cfg, ac, sc)
     assert rec.shape == z["rec"].shape and float((rec - torch.from_numpy(z["rec"])).abs().max() / np.abs(z["rec"]).max()) < 1e-5
+
+
+def test_bench_optional_legs_respect_the_wall_clock_budget():
+    """bench.run_leg: an optional leg is skipped (and says so) once the invocation has used its wall-clock budget, a failing leg is
+    recorded without taking the line down, a finished leg carries its wall time."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class Ctx:
+        budget_s = 1.0
+
+        def __init__(self, over):
+            self.over = over
+
+        def over_budget(self):
+            return self.over
+
+        def elapsed_s(self):
+            return 2.0 if self.over else 0.5
+    sec = {}
+    bench.run_leg(Ctx(True), sec, "late", lambda: dict(value=1))
+    assert "skipped" in sec["late"] and "value" not in sec["late"]
+    bench.run_leg(Ctx(False), sec, "ok", lambda: dict(value=3))
+    assert sec["ok"]["value"] == 3 and "leg_wall_s" in sec["ok"]
+
+    def boom():
+        raise ValueError("x")
+    bench.run_leg(Ctx(False), sec, "bad", boom)
+    assert "ValueError" in sec["bad"]["error"]
