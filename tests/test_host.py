@@ -452,7 +452,9 @@ def test_oracle_tokenizer_chain_matches_reference_fixture():
 def test_bench_optional_legs_respect_the_wall_clock_budget():
     """bench.run_leg: an optional leg is skipped (and says so) once the invocation has used its wall-clock budget, a failing leg is
     recorded without taking the line down, a finished leg carries its wall time."""
-    sys.path.insert(0, ROOT)
+    import sys
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
     import bench
 
     class Ctx:
